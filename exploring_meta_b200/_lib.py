@@ -1,0 +1,129 @@
+"""ctypes binding of libxmeta.so (the C ABI declared in include/xmeta.h).
+
+There is no fallback: if the shared library is missing ``load()`` raises, and every product path
+that computes anything goes through ``load()``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_double, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libxmeta.so')
+
+XM_CONV_FWD, XM_CONV_DGRAD = 0, 1
+XM_STAT_NONE, XM_STAT_SUM_SQ, XM_STAT_SUM_AUX = 0, 1, 2
+
+
+class XmBlockGeom(Structure):
+    _fields_ = [('tasks', c_int32), ('n', c_int32), ('cin', c_int32), ('cout', c_int32),
+                ('hin', c_int32), ('win', c_int32), ('hz', c_int32), ('wz', c_int32),
+                ('hp', c_int32), ('wp', c_int32), ('stride', c_int32), ('pool', c_int32)]
+
+
+class XmConvArgs(Structure):
+    _fields_ = [('g', XmBlockGeom), ('mode', c_int32), ('src_nchw', c_int32),
+                ('row0', c_int32), ('row_step', c_int32), ('rows_per_task', c_int32),
+                ('stat_mode', c_int32),
+                ('src1', c_void_p), ('w1', c_void_p), ('w1_task_stride', c_int64),
+                ('src2', c_void_p), ('w2', c_void_p), ('w2_task_stride', c_int64),
+                ('out', c_void_p), ('aux', c_void_p), ('stats', c_void_p)]
+
+
+class XmWgradArgs(Structure):
+    _fields_ = [('g', XmBlockGeom), ('src_nchw', c_int32), ('row0', c_int32), ('row_step', c_int32),
+                ('rows_per_task', c_int32),
+                ('x1', c_void_p), ('g1', c_void_p), ('x2', c_void_p), ('g2', c_void_p),
+                ('out_w', c_void_p), ('out_b', c_void_p), ('out_task_stride', c_int64),
+                ('base_w', c_void_p), ('base_b', c_void_p), ('base_task_stride', c_int64),
+                ('scale', c_float), ('partial', c_void_p), ('partial_bytes', c_int64)]
+
+
+class XmBnArgs(Structure):
+    _fields_ = [('g', XmBlockGeom), ('eps', c_float),
+                ('z', c_void_p), ('zdot', c_void_p), ('sums', c_void_p), ('dsums', c_void_p),
+                ('gamma', c_void_p), ('beta', c_void_p), ('gb_task_stride', c_int64),
+                ('gamma_dot', c_void_p), ('beta_dot', c_void_p), ('gbdot_task_stride', c_int64),
+                ('mean_invstd', c_void_p), ('call_stats', c_void_p), ('bwd_red', c_void_p),
+                ('dual_red', c_void_p),
+                ('p', c_void_p), ('pdot', c_void_p), ('gp', c_void_p), ('gpdot', c_void_p),
+                ('gz', c_void_p), ('gzdot', c_void_p),
+                ('out_gamma', c_void_p), ('out_beta', c_void_p), ('out_task_stride', c_int64),
+                ('base_gamma', c_void_p), ('base_beta', c_void_p), ('base_task_stride', c_int64),
+                ('scale', c_float), ('scratch', c_void_p)]
+
+
+class XmHeadArgs(Structure):
+    _fields_ = [('tasks', c_int32), ('n', c_int32), ('ways', c_int32), ('c', c_int32), ('hw', c_int32),
+                ('mode', c_int32), ('dual', c_int32),
+                ('feat', c_void_p), ('feat_dot', c_void_p),
+                ('labels', c_void_p), ('label_row0', c_int32), ('label_row_step', c_int32),
+                ('labels_per_task', c_int32),
+                ('w', c_void_p), ('b', c_void_p), ('wb_task_stride', c_int64),
+                ('w_dot', c_void_p), ('b_dot', c_void_p), ('wbdot_task_stride', c_int64),
+                ('loss', c_void_p), ('correct', c_void_p), ('logits', c_void_p),
+                ('g_feat', c_void_p), ('g_feat_dot', c_void_p),
+                ('out_w', c_void_p), ('out_b', c_void_p), ('out_task_stride', c_int64),
+                ('base_w', c_void_p), ('base_b', c_void_p), ('base_task_stride', c_int64),
+                ('scale', c_float)]
+
+
+class XmAnilHeadArgs(Structure):
+    _fields_ = [('tasks', c_int32), ('rows', c_int32), ('ways', c_int32), ('c', c_int32), ('hw', c_int32),
+                ('mode', c_int32), ('steps', c_int32), ('first_order', c_int32), ('lr', c_float),
+                ('feat', c_void_p), ('labels', c_void_p), ('w', c_void_p), ('b', c_void_p),
+                ('loss', c_void_p), ('correct', c_void_p), ('g_feat', c_void_p),
+                ('g_w', c_void_p), ('g_b', c_void_p), ('g_task_stride', c_int64),
+                ('scratch', c_void_p), ('scratch_bytes', c_int64)]
+
+
+# name -> (restype, argtypes): every symbol include/xmeta.h declares.
+SYMBOLS = {
+    'xm_conv': (c_int32, [POINTER(XmConvArgs), c_void_p]),
+    'xm_wgrad_scratch_bytes': (c_int64, [POINTER(XmBlockGeom)]),
+    'xm_wgrad': (c_int32, [POINTER(XmWgradArgs), c_void_p]),
+    'xm_bn_scratch_bytes': (c_int64, [POINTER(XmBlockGeom)]),
+    'xm_bn_fwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
+    'xm_bn_bwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
+    'xm_bn_dual_fwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
+    'xm_bn_dual_bwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
+    'xm_head': (c_int32, [POINTER(XmHeadArgs), c_void_p]),
+    'xm_anil_head_scratch_bytes': (c_int64, [POINTER(XmAnilHeadArgs)]),
+    'xm_anil_head': (c_int32, [POINTER(XmAnilHeadArgs), c_void_p]),
+    'xm_accumulate_tasks': (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p]),
+    'xm_adam_step': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                               c_float, c_float, c_float, c_int32, c_void_p]),
+    'xm_bn_ema': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int32,
+                            c_float, c_void_p]),
+    'xm_version': (c_int32, []),
+    'xm_last_error': (ctypes.c_char_p, []),
+    'xm_launch_count': (c_int64, []),
+}
+
+_lib = None
+
+
+class XmetaError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libxmeta.so (built by ``__graft_entry__.build()`` / ``python -m exploring_meta_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise XmetaError('libxmeta.so not found at %s -- build it with `python -m exploring_meta_b200.build` '
+                         '(there is no CPU or PyTorch fallback)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().xm_last_error()
+        raise XmetaError('%s failed (code %d): %s' % (what, code, msg.decode() if msg else ''))

@@ -1,0 +1,493 @@
+"""Task-batched MAML / ANIL meta-gradient engine: host-side launch programs over libxmeta's kernels.
+
+One ``MamlEngine.run()`` replaces the body of the reference's per-task Python loop
+(``vision/maml_vision.py:102-114``: ``maml.clone()`` -> ``fast_adapt`` -> ``eval_loss.backward()``) for a
+whole shard of tasks at once; every task carries its own fast weights.  The second-order term is
+computed forward-over-reverse: with theta_{t+1} = theta_t - lr * g(theta_t) the outer cotangent obeys
+``bar_t = bar_{t+1} - lr * H(theta_t) bar_{t+1}`` and, the Hessian being symmetric, ``H v`` is the tangent of
+the gradient computation in direction v.  Each inner step therefore costs one tangent ("dual")
+forward+backward sweep that re-uses the activations saved by the primal sweep -- same algorithmic
+FLOPs as the reference's reverse-over-reverse graph, a fraction of its memory
+traffic and ~100x fewer launches.
+
+The engine is a *static launch program*: all buffers are allocated once, every kernel argument
+block is built once, and ``run()`` only replays the list -- so the whole iteration can be captured
+into a CUDA graph (``capture()``).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (XM_CONV_DGRAD, XM_CONV_FWD, XM_STAT_NONE, XM_STAT_SUM_AUX, XM_STAT_SUM_SQ,
+                   XmAnilHeadArgs, XmBlockGeom, XmBnArgs, XmConvArgs, XmHeadArgs, XmWgradArgs)
+
+BN_EPS = 1e-5          # torch.nn.BatchNorm2d default, vision_models.py:168-174
+BN_MOMENTUM = 0.1
+
+
+def _require_cuda(device):
+    if device.type != 'cuda':
+        raise _lib.XmetaError('exploring_meta_b200 runs on CUDA devices only (got %s); there is no CPU path' % device)
+
+
+def _p(t, off=0):
+    """Device address of element ``off`` of a float32 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr() + off * t.element_size()
+
+
+class _Program:
+    """A recorded list of C-ABI calls: (function, argument block)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.calls = []
+
+    def emit(self, name, args):
+        self.calls.append((getattr(self.lib, name), args, name))
+
+    def emit_raw(self, name, *argv):
+        self.calls.append((getattr(self.lib, name), argv, name))
+
+    def replay(self, stream):
+        for fn, args, name in self.calls:
+            if isinstance(args, tuple):
+                code = fn(*args, stream)
+            else:
+                code = fn(ctypes.byref(args), stream)
+            if code != 0:
+                _lib.check(code, name)
+
+
+class _EngineBase:
+    def __init__(self, spec, tasks, device):
+        self.spec = spec
+        self.tasks = int(tasks)
+        self.device = torch.device(device)
+        _require_cuda(self.device)
+        self.lib = _lib.load()
+        self.dims = spec.block_dims()
+        self.C = spec.hidden
+        self.offs, self.P = spec.param_offsets()
+        self._graph = None
+
+    # ---- allocation helpers -------------------------------------------------------------------
+    def _f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def _f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+    def geom(self, l, n):
+        cin, hin, win, hz, wz, hp, wp = self.dims[l]
+        return XmBlockGeom(self.tasks, n, cin, self.C, hin, win, hz, wz, hp, wp,
+                           1 if self.spec.pool else 2, 1 if self.spec.pool else 0)
+
+    def zshape(self, l, n):
+        _, _, _, hz, wz, _, _ = self.dims[l]
+        return (self.tasks, n, hz, wz, self.C)
+
+    def pshape(self, l, n):
+        _, _, _, _, _, hp, wp = self.dims[l]
+        return (self.tasks, n, hp, wp, self.C)
+
+    def _alloc_common(self, nmax):
+        L = self.spec.layers
+        self.sums = self._f64(self.tasks, 2, self.C)
+        self.dsums = self._f64(self.tasks, 2, self.C)
+        g0 = self.geom(0, nmax)
+        nbytes = max(int(self.lib.xm_bn_scratch_bytes(ctypes.byref(self.geom(l, nmax)))) for l in range(L))
+        self.bn_scratch = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=self.device)
+        wbytes = max(int(self.lib.xm_wgrad_scratch_bytes(ctypes.byref(self.geom(l, nmax)))) for l in range(L))
+        self.wg_partial = torch.empty(max(wbytes, 4) // 4, dtype=torch.float32, device=self.device)
+        del g0
+
+    # ---- emitters shared by the MAML and ANIL programs --------------------------------------
+    def _emit_block_fwd(self, prog, l, n, src, img, theta, tstride, Z, Pout, MI, call_stats):
+        """conv -> batch statistics -> normalise + ReLU + pool   (ConvBlock.forward, vision_models.py:188-193)."""
+        o = self.offs
+        a = XmConvArgs()
+        a.g = self.geom(l, n)
+        a.mode = XM_CONV_FWD
+        a.stat_mode = XM_STAT_SUM_SQ
+        if l == 0:
+            a.src_nchw, a.row0, a.row_step, a.rows_per_task = 1, img[0], img[1], img[2]
+            a.src1 = _p(self.x)
+        else:
+            a.src1 = _p(src)
+        a.w1, a.w1_task_stride = _p(theta, o[4 * l + 2]), tstride
+        a.out, a.stats = _p(Z), _p(self.sums)
+        prog.emit('xm_conv', a)
+        b = XmBnArgs()
+        b.g, b.eps = self.geom(l, n), BN_EPS
+        b.z, b.sums = _p(Z), _p(self.sums)
+        b.gamma, b.beta, b.gb_task_stride = _p(theta, o[4 * l]), _p(theta, o[4 * l + 1]), tstride
+        b.mean_invstd, b.call_stats, b.p = _p(MI), _p(call_stats), _p(Pout)
+        b.scratch = _p(self.bn_scratch)
+        prog.emit('xm_bn_fwd', b)
+
+    def _emit_block_bwd(self, prog, l, n, xin, img, theta, tstride, Z, GP, MI, BR, GZ, GPprev,
+                        out, out_stride, base, base_stride, scale):
+        """BN/ReLU/pool backward -> dgrad -> wgrad, parameter gradients through the axpy epilogue."""
+        o = self.offs
+        b = XmBnArgs()
+        b.g, b.eps = self.geom(l, n), BN_EPS
+        b.z, b.gp, b.mean_invstd, b.bwd_red, b.gz = _p(Z), _p(GP), _p(MI), _p(BR), _p(GZ)
+        b.gamma, b.beta, b.gb_task_stride = _p(theta, o[4 * l]), _p(theta, o[4 * l + 1]), tstride
+        b.out_gamma, b.out_beta, b.out_task_stride = _p(out, o[4 * l]), _p(out, o[4 * l + 1]), out_stride
+        b.base_gamma, b.base_beta = _p(base, o[4 * l]), _p(base, o[4 * l + 1])
+        b.base_task_stride, b.scale = base_stride, scale
+        b.scratch = _p(self.bn_scratch)
+        prog.emit('xm_bn_bwd', b)
+        if l > 0:
+            d = XmConvArgs()
+            d.g, d.mode, d.stat_mode = self.geom(l, n), XM_CONV_DGRAD, XM_STAT_NONE
+            d.src1, d.w1, d.w1_task_stride = _p(GZ), _p(theta, o[4 * l + 2]), tstride
+            d.out = _p(GPprev)
+            prog.emit('xm_conv', d)
+        w = XmWgradArgs()
+        w.g = self.geom(l, n)
+        if l == 0:
+            w.src_nchw, w.row0, w.row_step, w.rows_per_task = 1, img[0], img[1], img[2]
+            w.x1 = _p(self.x)
+        else:
+            w.x1 = _p(xin)
+        w.g1 = _p(GZ)
+        w.out_w, w.out_b, w.out_task_stride = _p(out, o[4 * l + 2]), _p(out, o[4 * l + 3]), out_stride
+        w.base_w, w.base_b, w.base_task_stride = _p(base, o[4 * l + 2]), _p(base, o[4 * l + 3]), base_stride
+        w.scale = scale
+        w.partial, w.partial_bytes = _p(self.wg_partial), self.wg_partial.numel() * 4
+        prog.emit('xm_wgrad', w)
+
+    # ---- execution ----------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
+
+    def launch(self):
+        """Replays the program on the current stream (asynchronous)."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self.prog.replay(self._stream())
+
+    def capture(self):
+        """Captures the launch program into a CUDA graph; subsequent ``launch()`` calls replay it."""
+        if self._graph is not None:
+            return
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.prog.replay(side.cuda_stream)          # warm-up outside capture
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.prog.replay(torch.cuda.current_stream(self.device).cuda_stream)
+        self._graph = graph
+
+    @property
+    def launches_per_run(self):
+        return len(self.prog.calls)
+
+
+class MamlEngine(_EngineBase):
+    """Meta-gradient of ``tasks`` MAML tasks (second-order by default), all buffers static.
+
+    Inputs are written by the caller into ``x`` [tasks, 2S, C, H, W] (support = even rows, query = odd
+    rows, as ``prepare_batch`` splits them), ``y`` [tasks, 2S] int64 and ``theta`` [P] (master
+    parameters, ``parameters()`` order).  After ``launch()``:
+      ``grad``       [P]      sum over tasks of d(query loss)/d(theta)      (NOT yet scaled by 1/B)
+      ``loss``       [tasks]  query loss after adaptation (``fast_adapt``'s valid_loss)
+      ``correct``    [tasks]  int32 argmax==label count (``accuracy`` * Q)
+      ``theta_steps``[steps, tasks, P]  adapted fast weights theta_1..theta_T
+      ``call_stats`` [steps+1, layers, tasks, 2, C]  BN batch mean / unbiased var of every forward call
+    ``mode``: 'second' (reference default), 'first' (first_order=True), 'eval' (adapt + query metrics
+    only: the validation / meta-test pass of maml_vision.py:117-124 and core_functions/vision.py:26-42).
+    """
+
+    def __init__(self, spec, tasks, shots, steps, inner_lr, mode='second', device='cuda'):
+        super().__init__(spec, tasks, device)
+        assert mode in ('second', 'first', 'eval')
+        assert spec.head in ('flatten', 'mean')
+        self.shots, self.steps, self.lr, self.mode = int(shots), int(steps), float(inner_lr), mode
+        self.S = spec.ways * self.shots
+        self.rows = 2 * self.S
+        B, T, L, C, P = self.tasks, self.steps, spec.layers, self.C, self.P
+        S = self.S
+        self.x = self._f32(B, self.rows, spec.in_c, spec.in_h, spec.in_w)
+        self.y = torch.zeros((B, self.rows), dtype=torch.int64, device=self.device)
+        self.theta = self._f32(P)
+        self.grad = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros(B, dtype=torch.float32, device=self.device)
+        self.correct = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self.theta_steps = self._f32(max(T, 1), B, P)
+        self.call_stats = torch.zeros((T + 1, L, B, 2, C), dtype=torch.float32, device=self.device)
+        self._alloc_common(S)
+        keep = T if mode == 'second' else 1           # per-step activations are only re-read by the dual sweep
+        self.Z = [[self._f32(*self.zshape(l, S)) for l in range(L)] for _ in range(keep)]
+        self.Pa = [[self._f32(*self.pshape(l, S)) for l in range(L)] for _ in range(keep)]
+        self.GP = [[self._f32(*self.pshape(l, S)) for l in range(L)] for _ in range(keep)]
+        self.MI = [[self._f32(B, 2, C) for l in range(L)] for _ in range(keep)]
+        self.BR = [[self._f32(B, 2, C) for l in range(L)] for _ in range(keep)]
+        # temporaries: query pass (phase 2) and dual sweep (phase 3) share them
+        self.tZ = [self._f32(*self.zshape(l, S)) for l in range(L)]
+        self.tP = [self._f32(*self.pshape(l, S)) for l in range(L)]
+        self.tGP = [self._f32(*self.pshape(l, S)) for l in range(L)]
+        self.tMI = [self._f32(B, 2, C) for l in range(L)]
+        self.tBR = [self._f32(B, 2, C) for l in range(L)]
+        self.tDR = [self._f32(B, 2, C) for l in range(L)]
+        zmax = max(self.tZ[l].numel() for l in range(L))
+        self.GZ = self._f32(zmax)
+        self.GZdot = self._f32(zmax) if mode == 'second' else None
+        self.bar = [self._f32(B, P), self._f32(B, P)] if mode != 'eval' else None
+        self.prog = _Program(self.lib)
+        self._build()
+
+    # theta_t as (tensor, task stride): theta_0 is the shared master vector
+    def _theta(self, t):
+        if t == 0:
+            return self.theta, 0
+        return self.theta_steps[t - 1], self.P
+
+    def _emit_head(self, prog, n, feat, theta, tstride, label_row0, GPout, out, out_stride, base,
+                   base_stride, scale, loss=None, correct=None, dual=None):
+        o = self.offs
+        hp, wp = self.spec.out_hw()
+        h = XmHeadArgs()
+        h.tasks, h.n, h.ways, h.c, h.hw = self.tasks, n, self.spec.ways, self.C, hp * wp
+        h.mode = 0 if self.spec.head == 'flatten' else 1
+        h.feat = _p(feat)
+        h.labels, h.label_row0, h.label_row_step, h.labels_per_task = _p(self.y), label_row0, 2, self.rows
+        L4 = 4 * self.spec.layers
+        h.w, h.b, h.wb_task_stride = _p(theta, o[L4]), _p(theta, o[L4 + 1]), tstride
+        h.loss, h.correct = _p(loss), _p(correct)
+        if dual is None:
+            h.dual = 0
+            h.g_feat = _p(GPout)
+        else:
+            featdot, v = dual
+            h.dual = 1
+            h.feat_dot = _p(featdot)
+            h.w_dot, h.b_dot, h.wbdot_task_stride = _p(v, o[L4]), _p(v, o[L4 + 1]), self.P
+            h.g_feat_dot = _p(GPout)
+        if out is not None:
+            h.out_w, h.out_b, h.out_task_stride = _p(out, o[L4]), _p(out, o[L4 + 1]), out_stride
+            h.base_w, h.base_b = _p(base, o[L4]), _p(base, o[L4 + 1])
+            h.base_task_stride, h.scale = base_stride, scale
+        prog.emit('xm_head', h)
+
+    def _build(self):
+        prog, L, T, S, P = self.prog, self.spec.layers, self.steps, self.S, self.P
+        sup, qry = (0, 2, self.rows), (1, 2, self.rows)
+        # ---- phase 1: T inner steps on the support rows (core_functions/vision.py:9-13) ----------
+        for t in range(T):
+            k = t if self.mode == 'second' else 0
+            th, ts = self._theta(t)
+            nxt = self.theta_steps[t]
+            for l in range(L):
+                self._emit_block_fwd(prog, l, S, self.Pa[k][l - 1] if l else None, sup, th, ts,
+                                     self.Z[k][l], self.Pa[k][l], self.MI[k][l], self.call_stats[t, l])
+            self._emit_head(prog, S, self.Pa[k][L - 1], th, ts, 0, self.GP[k][L - 1],
+                            nxt, P, th, ts, -self.lr)
+            for l in reversed(range(L)):
+                self._emit_block_bwd(prog, l, S, self.Pa[k][l - 1] if l else None, sup, th, ts,
+                                     self.Z[k][l], self.GP[k][l], self.MI[k][l], self.BR[k][l], self.GZ,
+                                     self.GP[k][l - 1] if l else None, nxt, P, th, ts, -self.lr)
+        # ---- phase 2: query loss / accuracy at theta_T (vision.py:15-17) and its gradient -----
+        th, ts = self._theta(T)
+        for l in range(L):
+            self._emit_block_fwd(prog, l, S, self.tP[l - 1] if l else None, qry, th, ts,
+                                 self.tZ[l], self.tP[l], self.tMI[l], self.call_stats[T, l])
+        if self.mode == 'eval':
+            self._emit_head(prog, S, self.tP[L - 1], th, ts, 1, None, None, 0, None, 0, 0.0,
+                            loss=self.loss, correct=self.correct)
+            return
+        bar = self.bar[0]
+        self._emit_head(prog, S, self.tP[L - 1], th, ts, 1, self.tGP[L - 1], bar, P, None, 0, 1.0,
+                        loss=self.loss, correct=self.correct)
+        for l in reversed(range(L)):
+            self._emit_block_bwd(prog, l, S, self.tP[l - 1] if l else None, qry, th, ts,
+                                 self.tZ[l], self.tGP[l], self.tMI[l], self.tBR[l], self.GZ,
+                                 self.tGP[l - 1] if l else None, bar, P, None, 0, 1.0)
+        # ---- phase 3: bar_t = bar_{t+1} - lr * H(theta_t) bar_{t+1}, t = T-1 .. 0 (second order) ----
+        cur = 0
+        if self.mode == 'second':
+            for t in reversed(range(T)):
+                self._emit_dual_step(prog, t, self.bar[cur], self.bar[1 - cur])
+                cur = 1 - cur
+        # ---- sum over tasks in task order = accumulation into the master .grad (maml_vision.py:112) --
+        prog.emit_raw('xm_accumulate_tasks', _p(self.bar[cur]), P, self.tasks, P, _p(self.grad), 0)
+
+    def _emit_dual_step(self, prog, t, v, out):
+        """Tangent sweep of inner step t in direction v (= cotangent of theta_{t+1}); writes
+        out = v - lr * d/d(eps) grad(theta_t + eps v)."""
+        L, S, P, o = self.spec.layers, self.S, self.P, self.offs
+        sup = (0, 2, self.rows)
+        th, ts = self._theta(t)
+        Z, Pa, GP, MI, BR = self.Z[t], self.Pa[t], self.GP[t], self.MI[t], self.BR[t]
+        for l in range(L):
+            a = XmConvArgs()
+            a.g, a.mode, a.stat_mode = self.geom(l, S), XM_CONV_FWD, XM_STAT_SUM_AUX
+            if l == 0:                       # images carry no tangent: zdot = conv(x, Wdot)
+                a.src_nchw, a.row0, a.row_step, a.rows_per_task = 1, sup[0], sup[1], sup[2]
+                a.src1 = _p(self.x)
+            else:
+                a.src1 = _p(Pa[l - 1])
+                a.src2, a.w2, a.w2_task_stride = _p(self.tP[l - 1]), _p(th, o[4 * l + 2]), ts
+            a.w1, a.w1_task_stride = _p(v, o[4 * l + 2]), P
+            a.out, a.aux, a.stats = _p(self.tZ[l]), _p(Z[l]), _p(self.dsums)
+            prog.emit('xm_conv', a)
+            b = XmBnArgs()
+            b.g, b.eps = self.geom(l, S), BN_EPS
+            b.z, b.zdot, b.dsums, b.mean_invstd = _p(Z[l]), _p(self.tZ[l]), _p(self.dsums), _p(MI[l])
+            b.gamma, b.beta, b.gb_task_stride = _p(th, o[4 * l]), _p(th, o[4 * l + 1]), ts
+            b.gamma_dot, b.beta_dot, b.gbdot_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
+            b.pdot, b.dual_red = _p(self.tP[l]), _p(self.tDR[l])
+            b.scratch = _p(self.bn_scratch)
+            prog.emit('xm_bn_dual_fwd', b)
+        self._emit_head(prog, S, Pa[L - 1], th, ts, 0, self.tGP[L - 1], out, P, v, P, -self.lr,
+                        dual=(self.tP[L - 1], v))
+        for l in reversed(range(L)):
+            b = XmBnArgs()
+            b.g, b.eps = self.geom(l, S), BN_EPS
+            b.z, b.zdot, b.gp, b.gpdot = _p(Z[l]), _p(self.tZ[l]), _p(GP[l]), _p(self.tGP[l])
+            b.mean_invstd, b.bwd_red, b.dual_red = _p(MI[l]), _p(BR[l]), _p(self.tDR[l])
+            b.gamma, b.beta, b.gb_task_stride = _p(th, o[4 * l]), _p(th, o[4 * l + 1]), ts
+            b.gamma_dot, b.beta_dot, b.gbdot_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
+            b.gz, b.gzdot = _p(self.GZ), _p(self.GZdot)
+            b.out_gamma, b.out_beta, b.out_task_stride = _p(out, o[4 * l]), _p(out, o[4 * l + 1]), P
+            b.base_gamma, b.base_beta, b.base_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
+            b.scale = -self.lr
+            b.scratch = _p(self.bn_scratch)
+            prog.emit('xm_bn_dual_bwd', b)
+            if l > 0:                        # gxdot = dgrad(gzdot, W) + dgrad(gz, Wdot)
+                d = XmConvArgs()
+                d.g, d.mode, d.stat_mode = self.geom(l, S), XM_CONV_DGRAD, XM_STAT_NONE
+                d.src1, d.w1, d.w1_task_stride = _p(self.GZdot), _p(th, o[4 * l + 2]), ts
+                d.src2, d.w2, d.w2_task_stride = _p(self.GZ), _p(v, o[4 * l + 2]), P
+                d.out = _p(self.tGP[l - 1])
+                prog.emit('xm_conv', d)
+            w = XmWgradArgs()                # gWdot = wgrad(x, gzdot) + wgrad(xdot, gz)
+            w.g = self.geom(l, S)
+            if l == 0:
+                w.src_nchw, w.row0, w.row_step, w.rows_per_task = 1, sup[0], sup[1], sup[2]
+                w.x1 = _p(self.x)
+            else:
+                w.x1 = _p(Pa[l - 1])
+                w.x2, w.g2 = _p(self.tP[l - 1]), _p(self.GZ)
+            w.g1 = _p(self.GZdot)
+            w.out_w, w.out_b, w.out_task_stride = _p(out, o[4 * l + 2]), _p(out, o[4 * l + 3]), P
+            w.base_w, w.base_b, w.base_task_stride = _p(v, o[4 * l + 2]), _p(v, o[4 * l + 3]), P
+            w.scale = -self.lr
+            w.partial, w.partial_bytes = _p(self.wg_partial), self.wg_partial.numel() * 4
+            prog.emit('xm_wgrad', w)
+
+    # ---- convenience ----------------------------------------------------------------------------
+    def run(self, x=None, y=None, theta=None):
+        """Copies the given inputs into the static buffers (any may be None = already in place) and
+        launches.  Returns ``(grad, loss, correct)`` views of the static output buffers."""
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if y is not None:
+            self.y.copy_(y, non_blocking=True)
+        if theta is not None:
+            self.theta.copy_(theta, non_blocking=True)
+        self.launch()
+        return self.grad, self.loss, self.correct
+
+    def update_running_stats(self, running_mean, running_var):
+        """Applies the BN running-statistics side effect of this shard's forward calls to the given
+        per-layer buffers, in the reference's order: task-major, then call (T support calls, 1 query)."""
+        T, L, B, C = self.steps, self.spec.layers, self.tasks, self.C
+        cs = self.call_stats
+        for l in range(L):
+            _lib.check(self.lib.xm_bn_ema(_p(running_mean[l]), _p(running_var[l]), _p(cs[0, l]),
+                                          B, 2 * C, T + 1, cs.stride(0), C, BN_MOMENTUM, self._stream()),
+                       'xm_bn_ema')
+        return B * (T + 1)
+
+
+class AnilEngine(_EngineBase):
+    """ANIL (``vision/anil_vision.py:109-122``): body forward once per task over all 2S rows with the
+    shared body weights (one BN batch per task, ``utils/data_pre.py:118-119``), head-only adaptation
+    in one kernel, then a first-order body backward.  Outputs: ``grad`` [P_body] and ``head_grad``
+    [ways*D + ways] (sums over tasks, unscaled), ``loss``, ``correct``, ``call_stats`` [layers, tasks, 2, C]."""
+
+    def __init__(self, spec, tasks, shots, steps, inner_lr, first_order=False, device='cuda'):
+        super().__init__(spec, tasks, device)
+        assert spec.head == 'none'
+        self.shots, self.steps, self.lr = int(shots), int(steps), float(inner_lr)
+        self.first_order = bool(first_order)
+        self.S = spec.ways * self.shots
+        self.rows = 2 * self.S
+        B, L, C, P, R = self.tasks, spec.layers, self.C, self.P, self.rows
+        hp, wp = spec.out_hw()
+        self.D = C * hp * wp
+        self.PH = spec.ways * self.D + spec.ways
+        self.x = self._f32(B, R, spec.in_c, spec.in_h, spec.in_w)
+        self.y = torch.zeros((B, R), dtype=torch.int64, device=self.device)
+        self.theta = self._f32(P)
+        self.head = self._f32(self.PH)
+        self.grad = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self.head_grad = torch.zeros(self.PH, dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros(B, dtype=torch.float32, device=self.device)
+        self.correct = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self.call_stats = torch.zeros((L, B, 2, C), dtype=torch.float32, device=self.device)
+        self._alloc_common(R)
+        self.Z = [self._f32(*self.zshape(l, R)) for l in range(L)]
+        self.Pa = [self._f32(*self.pshape(l, R)) for l in range(L)]
+        self.GP = [self._f32(*self.pshape(l, R)) for l in range(L)]
+        self.MI = [self._f32(B, 2, C) for l in range(L)]
+        self.BR = [self._f32(B, 2, C) for l in range(L)]
+        self.GZ = self._f32(max(z.numel() for z in self.Z))
+        self.task_grad = self._f32(B, P)
+        self.task_head_grad = self._f32(B, self.PH)
+        self.prog = _Program(self.lib)
+        self._build()
+
+    def _build(self):
+        prog, L, B, P, R = self.prog, self.spec.layers, self.tasks, self.P, self.rows
+        rows = (0, 1, R)
+        for l in range(L):
+            self._emit_block_fwd(prog, l, R, self.Pa[l - 1] if l else None, rows, self.theta, 0,
+                                 self.Z[l], self.Pa[l], self.MI[l], self.call_stats[l])
+        hp, wp = self.spec.out_hw()
+        h = XmAnilHeadArgs()
+        h.tasks, h.rows, h.ways, h.c, h.hw, h.mode = B, R, self.spec.ways, self.C, hp * wp, 0
+        h.steps, h.first_order, h.lr = self.steps, int(self.first_order), self.lr
+        h.feat, h.labels = _p(self.Pa[L - 1]), _p(self.y)
+        h.w, h.b = _p(self.head), _p(self.head, self.spec.ways * self.D)
+        h.loss, h.correct, h.g_feat = _p(self.loss), _p(self.correct), _p(self.GP[L - 1])
+        h.g_w, h.g_b = _p(self.task_head_grad), _p(self.task_head_grad, self.spec.ways * self.D)
+        h.g_task_stride = self.PH
+        nbytes = int(self.lib.xm_anil_head_scratch_bytes(ctypes.byref(h)))
+        self.head_scratch = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=self.device)
+        h.scratch, h.scratch_bytes = _p(self.head_scratch), self.head_scratch.numel() * 4
+        prog.emit('xm_anil_head', h)
+        for l in reversed(range(L)):
+            self._emit_block_bwd(prog, l, R, self.Pa[l - 1] if l else None, rows, self.theta, 0,
+                                 self.Z[l], self.GP[l], self.MI[l], self.BR[l], self.GZ,
+                                 self.GP[l - 1] if l else None, self.task_grad, P, None, 0, 1.0)
+        prog.emit_raw('xm_accumulate_tasks', _p(self.task_grad), P, B, P, _p(self.grad), 0)
+        prog.emit_raw('xm_accumulate_tasks', _p(self.task_head_grad), self.PH, B, self.PH, _p(self.head_grad), 0)
+
+    def run(self, x=None, y=None, theta=None, head=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if y is not None:
+            self.y.copy_(y, non_blocking=True)
+        if theta is not None:
+            self.theta.copy_(theta, non_blocking=True)
+        if head is not None:
+            self.head.copy_(head, non_blocking=True)
+        self.launch()
+        return self.grad, self.head_grad, self.loss, self.correct
+
+    def update_running_stats(self, running_mean, running_var):
+        L, B, C = self.spec.layers, self.tasks, self.C
+        for l in range(L):
+            _lib.check(self.lib.xm_bn_ema(_p(running_mean[l]), _p(running_var[l]), _p(self.call_stats[l]),
+                                          B, 2 * C, 1, 0, C, BN_MOMENTUM, self._stream()), 'xm_bn_ema')
+        return B

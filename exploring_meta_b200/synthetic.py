@@ -1,0 +1,47 @@
+"""Seeded synthetic few-shot tasks of the reference's shapes.
+
+A task is what ``train_tasks.sample()`` returns in the reference (``vision/maml_vision.py:105``):
+``(data [2*k*w, C, H, W] float32, labels [2*k*w] int64)`` with samples grouped by class, 2k
+consecutive rows per class, so that ``prepare_batch`` (``utils/data_pre.py:115-129``) puts k rows of
+every class into the support set (even rows) and k into the query set (odd rows).
+
+Images are ``eps + 0.5 * prototype[label]`` with ``eps, prototype ~ N(0, 1)``: one prototype per
+class per task gives the inner loop a learnable signal.  Generation is on the CPU generator so the
+same seed yields the same bits in the build container, on the GPU box and in the fixtures.
+"""
+import torch
+
+
+def task_labels(ways, shots):
+    return torch.arange(ways, dtype=torch.int64).repeat_interleave(2 * shots)
+
+
+def make_tasks(tasks, ways, shots, in_shape, seed, dtype=torch.float32):
+    """Returns ``x [tasks, 2*k*w, C, H, W]`` and ``y [tasks, 2*k*w]`` on the CPU."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(int(seed))
+    y = task_labels(ways, shots)
+    proto = torch.randn((tasks, ways) + tuple(in_shape), generator=gen, dtype=torch.float32)
+    x = torch.randn((tasks, y.numel()) + tuple(in_shape), generator=gen, dtype=torch.float32)
+    x.add_(proto[:, y], alpha=0.5)
+    return x.to(dtype), y.unsqueeze(0).repeat(tasks, 1).contiguous()
+
+
+class SyntheticTasks:
+    """Stand-in for a learn2learn ``TaskDataset``: ``sample()`` returns one task, as the reference's
+    drivers and ``evaluate`` expect (``core_functions/vision.py:32``)."""
+
+    def __init__(self, ways, shots, in_shape, seed=0):
+        self.ways, self.shots, self.in_shape = ways, shots, tuple(in_shape)
+        self._seed = int(seed)
+        self._count = 0
+
+    def sample(self):
+        x, y = make_tasks(1, self.ways, self.shots, self.in_shape, self._seed + self._count)
+        self._count += 1
+        return x[0], y[0]
+
+    def sample_batch(self, tasks):
+        x, y = make_tasks(tasks, self.ways, self.shots, self.in_shape, self._seed + self._count)
+        self._count += tasks
+        return x, y

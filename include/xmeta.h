@@ -1,0 +1,206 @@
+/* xmeta.h -- C ABI of libxmeta.so: sm_100a kernels for the MAML / ANIL hot path of
+ * Kostis-S-Z/exploring_meta (task-batched inner-loop adaptation + second-order outer gradient).
+ *
+ * The reference has no FFI layer; its boundary is the Python API of core_functions/maml.py,
+ * core_functions/vision.py and core_functions/vision_models.py, and every FLOP below that API is an
+ * ATen library call.  Each entry point here replaces the ATen calls named in its comment
+ * (reference file:line = the call site that bottoms out in them).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All pointers are DEVICE pointers owned by the caller (PyTorch
+ *    allocations); the library never allocates or frees caller-visible memory.  Scratch comes from
+ *    caller-provided buffers whose sizes the *_scratch_bytes queries return.
+ *  - Every function returns 0 on success, <0 for an invalid argument (message via xm_last_error()),
+ *    >0 = cudaError_t of a failed launch.  No exceptions, no exit/abort.
+ *  - Every function is asynchronous on the given stream (cudaStream_t passed as void*), does no
+ *    host synchronisation and is CUDA-graph capturable.  No global mutable state except the
+ *    thread-local last-error string.
+ *  - "task" = one few-shot task of the meta-batch.  Every tensor carries a leading task dimension and
+ *    every parameter pointer a per-task stride in floats (stride 0 = all tasks share the master
+ *    weights, as at inner step 0 and for the ANIL body).
+ *  - Activations are NHWC fp32: [tasks][n][H][W][C].  User images stay in the reference's NCHW
+ *    layout [tasks][rows][C][H][W]; the first conv gathers rows row0, row0+row_step, ... directly
+ *    (this is prepare_batch's even/odd split, utils/data_pre.py:121-127, fused into the load).
+ *  - Parameters and their gradients use PyTorch's layouts ([cout][cin][3][3], [ways][D]) inside flat
+ *    per-task vectors in module.parameters() order (core_functions/vision_models.py:168-185: BN
+ *    weight, BN bias, conv weight, conv bias per block; then linear weight, bias).
+ *  - Parameter-gradient epilogue ("axpy epilogue"): kernels that produce a parameter gradient g write
+ *        out = (base ? base : 0) + scale * g
+ *    so that the inner SGD step theta' = theta - lr*g (learn2learn maml_update, called from
+ *    core_functions/vision.py:13) and the outer recursion are fused into the producing kernel.
+ */
+#ifndef XMETA_H_
+#define XMETA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM_VERSION 100
+
+/* Geometry of one ConvBlock call (core_functions/vision_models.py:149-193). */
+typedef struct XmBlockGeom {
+  int32_t tasks;      /* tasks in this launch                                          */
+  int32_t n;          /* images per task in this call (one BN batch)                   */
+  int32_t cin, cout;  /* conv channels                                                 */
+  int32_t hin, win;   /* block input spatial size                                      */
+  int32_t hz, wz;     /* conv output spatial size (pre-pool): stride 1 -> hin, 2 -> (hin+2-3)/2+1 */
+  int32_t hp, wp;     /* block output size: pool -> hz/2 (floor), else hz              */
+  int32_t stride;     /* 1 (max_pool=True) or 2 (max_pool=False), vision_models.py:158-167 */
+  int32_t pool;       /* 1: MaxPool2d(2,2,ceil_mode=False) after the ReLU              */
+} XmBlockGeom;
+
+enum { XM_CONV_FWD = 0, XM_CONV_DGRAD = 1 };
+enum { XM_STAT_NONE = 0, XM_STAT_SUM_SQ = 1, XM_STAT_SUM_AUX = 2 };
+
+/* xm_conv: 3x3 pad-1 cross-correlation as an implicit GEMM, per-task weights.
+ *   FWD  : out[t][n][hz][wz][cout] = conv(src1, w1) (+ conv(src2, w2))            src*: block inputs
+ *   DGRAD: out[t][n][hin][win][cin] = conv_transpose(src1, w1) (+ ...(src2, w2))  src*: [t][n][hz][wz][cout]
+ * The optional second (src, w) pair is the tangent term of the forward-over-reverse pass
+ * (zdot = conv(xdot, W) + conv(x, Wdot)).  Weights are PyTorch-layout [cout][cin][3][3]; the conv bias
+ * is never added (it is cancelled by train-mode BN: SURVEY fact 8).
+ * Epilogue statistics, accumulated in double per (task, channel) into stats[t][2][cout] (zeroed by
+ * the call): SUM_SQ -> {sum v, sum v^2} (BN batch statistics); SUM_AUX -> {sum v, sum v*aux}.
+ * Replaces aten::conv2d (vision_models.py:189), convolution_backward's dgrad and the conv terms of
+ * _convolution_double_backward (vision/maml_vision.py:112). */
+typedef struct XmConvArgs {
+  XmBlockGeom g;
+  int32_t mode;
+  int32_t src_nchw;                       /* 1: src1/src2 are user images (FWD only)   */
+  int32_t row0, row_step, rows_per_task;  /* image row selection when src_nchw         */
+  int32_t stat_mode;
+  const float* src1; const float* w1; int64_t w1_task_stride;
+  const float* src2; const float* w2; int64_t w2_task_stride;   /* src2 == NULL: one pair */
+  float* out;
+  const float* aux;                       /* SUM_AUX: tensor shaped like out           */
+  double* stats;
+} XmConvArgs;
+int xm_conv(const XmConvArgs* a, void* stream);
+
+/* xm_wgrad: weight gradient gW[co][ci][kh][kw] = sum_{n,h,w} x[n, s*h+kh-1, s*w+kw-1, ci] * g[n,h,w,co]
+ * (+ the same for an optional second (x, g) pair: Wdot-gradient = wgrad(x, gzdot) + wgrad(xdot, gz)),
+ * split over pixel ranges into `partial` and reduced in double, with the axpy epilogue writing
+ * out_w = base_w + scale*gW and out_b = base_b (the conv-bias gradient is analytically zero).
+ * Replaces convolution_backward's wgrad + learn2learn update_module's `p + (-lr*g)`. */
+typedef struct XmWgradArgs {
+  XmBlockGeom g;
+  int32_t src_nchw, row0, row_step, rows_per_task;
+  const float* x1; const float* g1;
+  const float* x2; const float* g2;       /* x2 == NULL: one pair                       */
+  float* out_w; float* out_b; int64_t out_task_stride;
+  const float* base_w; const float* base_b; int64_t base_task_stride;   /* NULL: zero base */
+  float scale;
+  float* partial; int64_t partial_bytes;  /* >= xm_wgrad_scratch_bytes(&g)              */
+} XmWgradArgs;
+int64_t xm_wgrad_scratch_bytes(const XmBlockGeom* g);
+int xm_wgrad(const XmWgradArgs* a, void* stream);
+
+/* BatchNorm(train mode, per-call batch statistics) + ReLU + MaxPool, forward / backward and the
+ * tangent ("dual") versions of both.  One argument block for the four entry points; each reads the
+ * fields its comment names.  Per-(task, channel) scalars live in small fp32 side buffers
+ * [tasks][2][cout] that travel between the calls of one block:
+ *   mean_invstd : {mean, 1/sqrt(var+eps)}            written by xm_bn_fwd
+ *   call_stats  : {mean, unbiased var}               written by xm_bn_fwd (running-stat EMA input)
+ *   bwd_red     : {<g>, <g*xhat>}                    written by xm_bn_bwd
+ *   dual_red    : {<zdot>, <zdot*xhat>}              written by xm_bn_dual_fwd
+ * Replaces native_batch_norm / relu / max_pool2d_with_indices (vision_models.py:190-192), their
+ * backward ops, and (dual pair) batchnorm_double_backward + the mask/gather double-backward ops. */
+typedef struct XmBnArgs {
+  XmBlockGeom g;
+  float eps;
+  const float* z; const float* zdot;            /* [t][n][hz][wz][cout]                        */
+  const double* sums;                           /* {sum z, sum z^2}      from xm_conv SUM_SQ     */
+  const double* dsums;                          /* {sum zdot, sum zdot*z} from xm_conv SUM_AUX   */
+  const float* gamma; const float* beta; int64_t gb_task_stride;
+  const float* gamma_dot; const float* beta_dot; int64_t gbdot_task_stride;
+  float* mean_invstd; float* call_stats; float* bwd_red; float* dual_red;
+  float* p; float* pdot;                        /* block outputs [t][n][hp][wp][cout]          */
+  const float* gp; const float* gpdot;          /* cotangents of p / tangent of gp (NULL = 0)  */
+  float* gz; float* gzdot;                      /* gradients w.r.t. z                          */
+  float* out_gamma; float* out_beta; int64_t out_task_stride;          /* axpy epilogue      */
+  const float* base_gamma; const float* base_beta; int64_t base_task_stride;
+  float scale;
+  double* scratch;                              /* >= xm_bn_scratch_bytes(&g)                  */
+} XmBnArgs;
+int64_t xm_bn_scratch_bytes(const XmBlockGeom* g);
+/* reads z, sums, gamma, beta                      writes p, mean_invstd, call_stats(opt) */
+int xm_bn_fwd(const XmBnArgs* a, void* stream);
+/* reads z, gp, mean_invstd, gamma, beta           writes gz, bwd_red, out_gamma/out_beta  */
+int xm_bn_bwd(const XmBnArgs* a, void* stream);
+/* reads z, zdot, dsums, mean_invstd, gamma(+dot), beta(+dot)   writes pdot, dual_red     */
+int xm_bn_dual_fwd(const XmBnArgs* a, void* stream);
+/* reads z, zdot, gp, gpdot, mean_invstd, bwd_red, dual_red, gamma(+dot), beta
+ * writes gz (recomputed), gzdot, out_gamma/out_beta = base + scale * tangent of (g_gamma, g_beta) */
+int xm_bn_dual_bwd(const XmBnArgs* a, void* stream);
+
+/* xm_head: classifier head on block-4 features, one CTA per task, forward + loss + backward fused.
+ *   mode 0 (MiniImagenetCNN.forward, vision_models.py:107-110): X = flatten in NCHW order, D = c*hw
+ *   mode 1 (OmniglotCNN.forward :51-55):                        X = mean over hw,           D = c
+ *   logits = X W^T + b ; loss = CrossEntropyLoss(mean) (vision/maml_vision.py:86) ; correct = #(argmax == y)
+ *   (core_functions/vision.py:21-23, lowest index wins ties).
+ * dual == 0: writes loss/correct/logits (each optional), g_feat = dL/dfeat and out_{w,b} = base + scale*dL/d{w,b}.
+ * dual == 1: additionally takes tangents (feat_dot, w_dot, b_dot), writes g_feat_dot = tangent of dL/dfeat and
+ *            out_{w,b} = base + scale * tangent of dL/d{w,b}   (softmax-CE Hessian term included).
+ * Replaces aten::linear + cross_entropy forward/backward/double-backward. */
+typedef struct XmHeadArgs {
+  int32_t tasks, n, ways, c, hw, mode, dual;
+  const float* feat; const float* feat_dot;      /* [t][n][hw][c] (feat_dot NULL = 0)           */
+  const int64_t* labels; int32_t label_row0, label_row_step, labels_per_task;
+  const float* w; const float* b; int64_t wb_task_stride;
+  const float* w_dot; const float* b_dot; int64_t wbdot_task_stride;
+  float* loss; int32_t* correct; float* logits;  /* [t], [t], [t][n][ways]; each may be NULL    */
+  float* g_feat; float* g_feat_dot;
+  float* out_w; float* out_b; int64_t out_task_stride;
+  const float* base_w; const float* base_b; int64_t base_task_stride;
+  float scale;
+} XmHeadArgs;
+int xm_head(const XmHeadArgs* a, void* stream);
+
+/* xm_anil_head: ANIL's head-only adaptation (vision/anil_vision.py:116-122 + core_functions/vision.py:9-17
+ * with features != None): per task, `steps` second-order (or first-order) inner steps of a Linear(D, ways)
+ * on the support feature rows (even rows), query loss / correct count on the odd rows, and the outer
+ * gradient w.r.t. the head initialisation (g_w, g_b: per task) and w.r.t. ALL feature rows (g_feat).
+ * feat is the body output for all rows of the task: [t][rows][hw][c], flattened like xm_head mode 0/1.
+ * scratch >= xm_anil_head_scratch_bytes(). */
+typedef struct XmAnilHeadArgs {
+  int32_t tasks, rows, ways, c, hw, mode, steps, first_order;
+  float lr;
+  const float* feat; const int64_t* labels;     /* [t][rows][hw][c], [t][rows]                 */
+  const float* w; const float* b;               /* shared head initialisation [ways][D], [ways] */
+  float* loss; int32_t* correct;                /* [t]                                         */
+  float* g_feat;                                /* [t][rows][hw][c]                            */
+  float* g_w; float* g_b; int64_t g_task_stride;
+  float* scratch; int64_t scratch_bytes;
+} XmAnilHeadArgs;
+int64_t xm_anil_head_scratch_bytes(const XmAnilHeadArgs* a);
+int xm_anil_head(const XmAnilHeadArgs* a, void* stream);
+
+/* dst[i] = (accumulate ? dst[i] : 0) + sum_t src[t*task_stride + i], tasks added in order in fp32 --
+ * the order in which eval_loss.backward() accumulates into the master .grad (vision/maml_vision.py:112). */
+int xm_accumulate_tasks(const float* src, int64_t task_stride, int32_t tasks, int64_t count,
+                        float* dst, int32_t accumulate, void* stream);
+
+/* Outer step (vision/maml_vision.py:139-141): g = grad*grad_scale (the 1/meta_batch_size), then
+ * torch.optim.Adam's update with bias correction for step number `step` (1-based), no weight decay. */
+int xm_adam_step(float* theta, const float* grad, float* m, float* v, int64_t count, float grad_scale,
+                 float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* BatchNorm running-statistics side effect, composed sequentially like the reference's shared
+ * buffers see it: for o in [0,n_outer) for i in [0,n_inner): r <- (1-m) r + m s(o,i), where
+ * s(o,i) = {mean[C], unbiased var[C]} at call_stats + o*outer_stride + i*inner_stride (floats). */
+int xm_bn_ema(float* running_mean, float* running_var, const float* call_stats, int32_t n_outer,
+              int64_t outer_stride, int32_t n_inner, int64_t inner_stride, int32_t channels,
+              float momentum, void* stream);
+
+int xm_version(void);
+const char* xm_last_error(void);
+/* Number of kernel launches this library has issued from the calling process (bench.py's gpu_launches). */
+int64_t xm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* XMETA_H_ */

@@ -1,0 +1,425 @@
+"""CPU emulator of the libxmeta C ABI (TEST INFRASTRUCTURE -- never imported by the product).
+
+Every function takes the same ctypes argument blocks as the real library, interprets the raw
+addresses as CPU tensors and evaluates the kernel's *contract* with plain torch ops.  Uses:
+  * ``-m "not gpu"`` tests run the product's host-side launch programs (exploring_meta_b200/engine.py)
+    against this emulator and compare with the oracle -- this checks the forward-over-reverse
+    algorithm, the buffer plumbing and the launch order without a GPU;
+  * ``-m gpu`` kernel tests use the same functions as the per-kernel reference for the CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_NP = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
+
+
+def view(addr, shape, dtype=torch.float32):
+    """A writable CPU tensor over raw memory at ``addr``."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    if n == 0:
+        return torch.empty(shape, dtype=dtype)
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    buf = (ctypes.c_char * (n * itemsize)).from_address(int(addr))
+    arr = np.frombuffer(buf, dtype=_NP[dtype], count=n)
+    return torch.from_numpy(arr).view(*shape)
+
+
+def param(addr, stride, tasks, shape):
+    """Per-task parameter tensor [tasks, *shape] gathered from ``addr + t*stride`` floats (a copy)."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return torch.stack([view(addr + 4 * t * stride, (n,)).clone().view(*shape) for t in range(tasks)])
+
+
+def write_param(addr, stride, tasks, value):
+    for t in range(tasks):
+        view(addr + 4 * t * stride, (value[t].numel(),)).copy_(value[t].reshape(-1))
+
+
+def axpy_out(out, out_stride, base, base_stride, scale, tasks, grad):
+    """out = (base ? base : 0) + scale * grad, per task."""
+    if not out:
+        return
+    shape = grad.shape[1:]
+    b = param(base, base_stride, tasks, shape) if base else torch.zeros_like(grad)
+    write_param(out, out_stride, tasks, b + scale * grad)
+
+
+def _nhwc_to_nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def _nchw_to_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _block_input(addr, g, nchw, row0, row_step, rows_per_task):
+    """Block input of every task as NCHW [tasks, n, cin, hin, win]."""
+    if nchw:
+        full = view(addr, (g.tasks, rows_per_task, g.cin, g.hin, g.win))
+        idx = torch.arange(g.n) * row_step + row0
+        return full[:, idx].clone()
+    x = view(addr, (g.tasks, g.n, g.hin, g.win, g.cin))
+    return x.permute(0, 1, 4, 2, 3).contiguous()
+
+
+def _sel_masks(a, z, mi, gamma, beta):
+    """xhat, y and the 0/1 selection mask (pool arg-max AND y > 0) for one BN call, NHWC per task."""
+    g = a.g
+    mean, invstd = mi[:, 0], mi[:, 1]
+    xhat = (z - mean[:, None, None, None, :]) * invstd[:, None, None, None, :]
+    y = gamma[:, None, None, None, :] * xhat + beta[:, None, None, None, :]
+    if not g.pool:
+        return xhat, y, (y > 0).to(z.dtype)
+    sel = torch.zeros_like(z)
+    for t in range(g.tasks):
+        act = F.relu(_nhwc_to_nchw(y[t]))
+        pooled, idx = F.max_pool2d(act, 2, 2, return_indices=True)
+        onehot = torch.zeros(act.shape[0], act.shape[1], g.hz * g.wz, dtype=z.dtype)
+        onehot.scatter_(2, idx.flatten(2), (pooled.flatten(2) > 0).to(z.dtype))
+        sel[t] = _nchw_to_nhwc(onehot.view(act.shape))
+    return xhat, y, sel
+
+
+def _up(gp, g):
+    """Cotangent of the pooled output scattered back to every position of its window (NHWC)."""
+    if not g.pool:
+        return gp
+    up = gp.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    return F.pad(up, (0, 0, 0, g.wz - 2 * g.wp, 0, g.hz - 2 * g.hp))
+
+
+def _down(v, g):
+    """Sum over each pooling window (exactly one selected element contributes)."""
+    if not g.pool:
+        return v
+    v = v[:, :, :2 * g.hp, :2 * g.wp]
+    return v.reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).sum(dim=(3, 5))
+
+
+def _mean(v):
+    return v.double().mean(dim=(1, 2, 3)).to(v.dtype)          # per (task, channel)
+
+
+def _bc(s):
+    return s[:, None, None, None, :]
+
+
+class EmulatedLib:
+    """Drop-in for the ctypes library object returned by ``exploring_meta_b200._lib.load()``."""
+
+    def __init__(self):
+        self.launches = 0
+        self._err = b''
+
+    @staticmethod
+    def _args(ref):
+        return ref._obj if hasattr(ref, '_obj') else ref
+
+    # ------------------------------------------------------------------ misc
+    def xm_version(self):
+        return 100
+
+    def xm_last_error(self):
+        return self._err
+
+    def xm_launch_count(self):
+        return self.launches
+
+    def xm_bn_scratch_bytes(self, ref):
+        g = self._args(ref)
+        return g.tasks * 4 * g.cout * 8
+
+    def xm_wgrad_scratch_bytes(self, ref):
+        g = self._args(ref)
+        return g.tasks * 9 * g.cin * g.cout * 4
+
+    # ------------------------------------------------------------------ conv
+    def xm_conv(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        out = None
+        for src, w, ws in ((a.src1, a.w1, a.w1_task_stride), (a.src2, a.w2, a.w2_task_stride)):
+            if not src:
+                continue
+            W = param(w, ws, g.tasks, (g.cout, g.cin, 3, 3))
+            if a.mode == 0:
+                x = _block_input(src, g, a.src_nchw, a.row0, a.row_step, a.rows_per_task)
+                r = torch.stack([F.conv2d(x[t], W[t], None, stride=g.stride, padding=1) for t in range(g.tasks)])
+            else:
+                gz = view(src, (g.tasks, g.n, g.hz, g.wz, g.cout)).permute(0, 1, 4, 2, 3).contiguous()
+                r = torch.stack([torch.nn.grad.conv2d_input((g.n, g.cin, g.hin, g.win), W[t], gz[t],
+                                                            stride=g.stride, padding=1) for t in range(g.tasks)])
+            out = r if out is None else out + r
+        out = out.permute(0, 1, 3, 4, 2).contiguous()          # NHWC
+        view(a.out, out.shape).copy_(out)
+        if a.stat_mode:
+            st = view(a.stats, (g.tasks, 2, out.shape[-1]), torch.float64)
+            st[:, 0] = out.double().sum(dim=(1, 2, 3))
+            other = out if a.stat_mode == 1 else view(a.aux, out.shape)
+            st[:, 1] = (out.double() * other.double()).sum(dim=(1, 2, 3))
+        return 0
+
+    def xm_wgrad(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 2
+        total = None
+        for xa, ga in ((a.x1, a.g1), (a.x2, a.g2)):
+            if not xa:
+                continue
+            x = _block_input(xa, g, a.src_nchw, a.row0, a.row_step, a.rows_per_task)
+            gz = view(ga, (g.tasks, g.n, g.hz, g.wz, g.cout)).permute(0, 1, 4, 2, 3).contiguous()
+            r = torch.stack([torch.nn.grad.conv2d_weight(x[t], (g.cout, g.cin, 3, 3), gz[t],
+                                                         stride=g.stride, padding=1) for t in range(g.tasks)])
+            total = r if total is None else total + r
+        axpy_out(a.out_w, a.out_task_stride, a.base_w, a.base_task_stride, a.scale, g.tasks, total)
+        axpy_out(a.out_b, a.out_task_stride, a.base_b, a.base_task_stride, 0.0, g.tasks,
+                 torch.zeros(g.tasks, g.cout))
+        return 0
+
+    # ------------------------------------------------------------------ BN + ReLU + pool
+    def _gb(self, a):
+        g = a.g
+        return (param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,)),
+                param(a.beta, a.gb_task_stride, g.tasks, (g.cout,)))
+
+    def xm_bn_fwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        z = view(a.z, (g.tasks, g.n, g.hz, g.wz, g.cout))
+        sums = view(a.sums, (g.tasks, 2, g.cout), torch.float64)
+        cnt = g.n * g.hz * g.wz
+        mean = sums[:, 0] / cnt
+        var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        mi[:, 0] = mean.float()
+        mi[:, 1] = (1.0 / torch.sqrt(var + a.eps)).float()
+        if a.call_stats:
+            cs = view(a.call_stats, (g.tasks, 2, g.cout))
+            cs[:, 0] = mean.float()
+            cs[:, 1] = (var * (cnt / max(cnt - 1, 1))).float()
+        gamma, beta = self._gb(a)
+        xhat, y, sel = _sel_masks(a, z, mi, gamma, beta)
+        act = F.relu(y)
+        if g.pool:
+            p = act[:, :, :2 * g.hp, :2 * g.wp].reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).amax(dim=(3, 5))
+        else:
+            p = act
+        view(a.p, p.shape).copy_(p)
+        return 0
+
+    def xm_bn_bwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 2
+        z = view(a.z, (g.tasks, g.n, g.hz, g.wz, g.cout))
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        gamma, beta = self._gb(a)
+        xhat, y, sel = _sel_masks(a, z, mi, gamma, beta)
+        gbn = sel * _up(view(a.gp, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
+        m1, m2 = _mean(gbn), _mean(gbn * xhat)
+        br = view(a.bwd_red, (g.tasks, 2, g.cout))
+        br[:, 0], br[:, 1] = m1, m2
+        gz = _bc(gamma * mi[:, 1]) * (gbn - _bc(m1) - xhat * _bc(m2))
+        view(a.gz, gz.shape).copy_(gz)
+        cnt = g.n * g.hz * g.wz
+        axpy_out(a.out_gamma, a.out_task_stride, a.base_gamma, a.base_task_stride, a.scale, g.tasks, m2 * cnt)
+        axpy_out(a.out_beta, a.out_task_stride, a.base_beta, a.base_task_stride, a.scale, g.tasks, m1 * cnt)
+        return 0
+
+    def xm_bn_dual_fwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        z = view(a.z, (g.tasks, g.n, g.hz, g.wz, g.cout))
+        zd = view(a.zdot, z.shape)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        ds = view(a.dsums, (g.tasks, 2, g.cout), torch.float64)
+        cnt = g.n * g.hz * g.wz
+        mean, r = mi[:, 0].double(), mi[:, 1].double()
+        d1 = ds[:, 0] / cnt
+        d2 = r * (ds[:, 1] / cnt - mean * d1)
+        dr = view(a.dual_red, (g.tasks, 2, g.cout))
+        dr[:, 0], dr[:, 1] = d1.float(), d2.float()
+        gamma, beta = self._gb(a)
+        gd = param(a.gamma_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        bd = param(a.beta_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        xhat, y, sel = _sel_masks(a, z, mi, gamma, beta)
+        xhd = _bc(mi[:, 1]) * (zd - _bc(dr[:, 0]) - xhat * _bc(dr[:, 1]))
+        yd = _bc(gd) * xhat + _bc(gamma) * xhd + _bc(bd)
+        pd = _down(sel * yd, g)
+        view(a.pdot, pd.shape).copy_(pd)
+        return 0
+
+    def xm_bn_dual_bwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 2
+        z = view(a.z, (g.tasks, g.n, g.hz, g.wz, g.cout))
+        zd = view(a.zdot, z.shape)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        br = view(a.bwd_red, (g.tasks, 2, g.cout))
+        dr = view(a.dual_red, (g.tasks, 2, g.cout))
+        gamma, beta = self._gb(a)
+        gd = param(a.gamma_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        xhat, y, sel = _sel_masks(a, z, mi, gamma, beta)
+        gbn = sel * _up(view(a.gp, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
+        if a.gpdot:
+            gbnd = sel * _up(view(a.gpdot, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
+        else:
+            gbnd = torch.zeros_like(gbn)
+        r, m1, m2, d1, d2 = mi[:, 1], br[:, 0], br[:, 1], dr[:, 0], dr[:, 1]
+        e1, e2, e3 = _mean(gbnd), _mean(gbnd * xhat), _mean(gbn * zd)
+        q = r * (e3 - d1 * m1 - d2 * m2)                 # <g * xhat_dot>
+        rdot = -r * r * d2
+        xhd = _bc(r) * (zd - _bc(d1) - xhat * _bc(d2))
+        proj = gbn - _bc(m1) - xhat * _bc(m2)
+        gz = _bc(gamma * r) * proj
+        gzd = _bc(gd * r + gamma * rdot) * proj + _bc(gamma * r) * (gbnd - _bc(e1) - xhd * _bc(m2) - xhat * _bc(e2 + q))
+        view(a.gz, gz.shape).copy_(gz)
+        view(a.gzdot, gzd.shape).copy_(gzd)
+        cnt = g.n * g.hz * g.wz
+        axpy_out(a.out_gamma, a.out_task_stride, a.base_gamma, a.base_task_stride, a.scale, g.tasks, (e2 + q) * cnt)
+        axpy_out(a.out_beta, a.out_task_stride, a.base_beta, a.base_task_stride, a.scale, g.tasks, e1 * cnt)
+        return 0
+
+    # ------------------------------------------------------------------ heads
+    @staticmethod
+    def _flatten_feat(f, mode):
+        """[tasks, n, hw, c] -> X [tasks, n, D]: NCHW flatten order (c major) or spatial mean."""
+        if mode == 0:
+            return f.permute(0, 1, 3, 2).reshape(f.shape[0], f.shape[1], -1)
+        return f.mean(dim=2)
+
+    @staticmethod
+    def _unflatten_grad(gx, mode, hw, c):
+        if mode == 0:
+            return gx.reshape(gx.shape[0], gx.shape[1], c, hw).permute(0, 1, 3, 2).contiguous()
+        return (gx / hw)[:, :, None, :].expand(-1, -1, hw, -1).contiguous()
+
+    def xm_head(self, ref, stream):
+        a = self._args(ref)
+        self.launches += 1
+        B, n, ways, c, hw = a.tasks, a.n, a.ways, a.c, a.hw
+        D = c * hw if a.mode == 0 else c
+        X = self._flatten_feat(view(a.feat, (B, n, hw, c)), a.mode)
+        W = param(a.w, a.wb_task_stride, B, (ways, D))
+        b = param(a.b, a.wb_task_stride, B, (ways,))
+        lab = view(a.labels, (B, a.labels_per_task), torch.int64)
+        ys = lab[:, torch.arange(n) * a.label_row_step + a.label_row0]
+        logits = torch.einsum('bnd,bwd->bnw', X, W) + b[:, None, :]
+        if a.logits:
+            view(a.logits, logits.shape).copy_(logits)
+        logp = F.log_softmax(logits, dim=2)
+        prob = logp.exp()
+        onehot = F.one_hot(ys, ways).to(prob.dtype)
+        if a.loss:
+            view(a.loss, (B,)).copy_(-(logp * onehot).sum(2).mean(1))
+        if a.correct:
+            view(a.correct, (B,), torch.int32).copy_((logits.argmax(2) == ys).sum(1).int())
+        gl = (prob - onehot) / n
+        if not a.dual:
+            gW, gb, gX = torch.einsum('bnw,bnd->bwd', gl, X), gl.sum(1), torch.einsum('bnw,bwd->bnd', gl, W)
+            if a.g_feat:
+                view(a.g_feat, (B, n, hw, c)).copy_(self._unflatten_grad(gX, a.mode, hw, c))
+        else:
+            Xd = self._flatten_feat(view(a.feat_dot, (B, n, hw, c)), a.mode) if a.feat_dot else torch.zeros_like(X)
+            Wd = param(a.w_dot, a.wbdot_task_stride, B, (ways, D))
+            bd = param(a.b_dot, a.wbdot_task_stride, B, (ways,))
+            ld = torch.einsum('bnd,bwd->bnw', Xd, W) + torch.einsum('bnd,bwd->bnw', X, Wd) + bd[:, None, :]
+            gld = prob * (ld - (prob * ld).sum(2, keepdim=True)) / n
+            gW = torch.einsum('bnw,bnd->bwd', gld, X) + torch.einsum('bnw,bnd->bwd', gl, Xd)
+            gb = gld.sum(1)
+            gX = torch.einsum('bnw,bwd->bnd', gld, W) + torch.einsum('bnw,bwd->bnd', gl, Wd)
+            if a.g_feat_dot:
+                view(a.g_feat_dot, (B, n, hw, c)).copy_(self._unflatten_grad(gX, a.mode, hw, c))
+        axpy_out(a.out_w, a.out_task_stride, a.base_w, a.base_task_stride, a.scale, B, gW)
+        axpy_out(a.out_b, a.out_task_stride, a.base_b, a.base_task_stride, a.scale, B, gb)
+        return 0
+
+    def xm_anil_head_scratch_bytes(self, ref):
+        a = self._args(ref)
+        return a.tasks * (a.steps + 1) * (a.ways * (a.c * a.hw if a.mode == 0 else a.c) + a.ways) * 4
+
+    def xm_anil_head(self, ref, stream):
+        a = self._args(ref)
+        self.launches += 1
+        B, R, ways, c, hw = a.tasks, a.rows, a.ways, a.c, a.hw
+        D = c * hw if a.mode == 0 else c
+        X = self._flatten_feat(view(a.feat, (B, R, hw, c)), a.mode)
+        lab = view(a.labels, (B, R), torch.int64)
+        Fs, Fq, ys, yq = X[:, 0::2], X[:, 1::2], lab[:, 0::2], lab[:, 1::2]
+        S, Q = Fs.shape[1], Fq.shape[1]
+        W = view(a.w, (ways, D)).clone()[None].repeat(B, 1, 1)
+        b = view(a.b, (ways,)).clone()[None].repeat(B, 1)
+        Ys, Yq = F.one_hot(ys, ways).float(), F.one_hot(yq, ways).float()
+        Ws, bs, gls, ps = [W], [b], [], []
+        for _ in range(a.steps):
+            p = F.softmax(torch.einsum('bnd,bwd->bnw', Fs, Ws[-1]) + bs[-1][:, None], dim=2)
+            gl = (p - Ys) / S
+            ps.append(p)
+            gls.append(gl)
+            Ws.append(Ws[-1] - a.lr * torch.einsum('bnw,bnd->bwd', gl, Fs))
+            bs.append(bs[-1] - a.lr * gl.sum(1))
+        lq = torch.einsum('bnd,bwd->bnw', Fq, Ws[-1]) + bs[-1][:, None]
+        logp = F.log_softmax(lq, dim=2)
+        view(a.loss, (B,)).copy_(-(logp * Yq).sum(2).mean(1))
+        view(a.correct, (B,), torch.int32).copy_((lq.argmax(2) == yq).sum(1).int())
+        glq = (logp.exp() - Yq) / Q
+        Wb, bb = torch.einsum('bnw,bnd->bwd', glq, Fq), glq.sum(1)
+        gFq = torch.einsum('bnw,bwd->bnd', glq, Ws[-1])
+        gFs = torch.zeros_like(Fs)
+        if not a.first_order:
+            for t in reversed(range(a.steps)):
+                uW, ub = -a.lr * Wb, -a.lr * bb
+                cot = torch.einsum('bnd,bwd->bnw', Fs, uW) + ub[:, None]
+                gFs = gFs + torch.einsum('bnw,bwd->bnd', gls[t], uW)
+                dl = ps[t] * (cot - (ps[t] * cot).sum(2, keepdim=True)) / S
+                Wb = Wb + torch.einsum('bnw,bnd->bwd', dl, Fs)
+                bb = bb + dl.sum(1)
+                gFs = gFs + torch.einsum('bnw,bwd->bnd', dl, Ws[t])
+        gX = torch.zeros_like(X)
+        gX[:, 0::2], gX[:, 1::2] = gFs, gFq
+        view(a.g_feat, (B, R, hw, c)).copy_(self._unflatten_grad(gX, a.mode, hw, c))
+        write_param(a.g_w, a.g_task_stride, B, Wb)
+        write_param(a.g_b, a.g_task_stride, B, bb)
+        return 0
+
+    # ------------------------------------------------------------------ outer-step helpers
+    def xm_accumulate_tasks(self, src, task_stride, tasks, count, dst, accumulate, stream):
+        self.launches += 1
+        d = view(dst, (count,))
+        acc = d.clone() if accumulate else torch.zeros(count)
+        for t in range(tasks):
+            acc = acc + view(src + 4 * t * task_stride, (count,))
+        d.copy_(acc)
+        return 0
+
+    def xm_adam_step(self, theta, grad, m, v, count, grad_scale, lr, beta1, beta2, eps, step, stream):
+        self.launches += 1
+        th, g, mm, vv = (view(p, (count,)) for p in (theta, grad, m, v))
+        gs = g * grad_scale
+        mm.copy_(beta1 * mm + (1 - beta1) * gs)
+        vv.copy_(beta2 * vv + (1 - beta2) * gs * gs)
+        denom = vv.sqrt() / (1 - beta2 ** step) ** 0.5 + eps
+        th.copy_(th - (lr / (1 - beta1 ** step)) * mm / denom)
+        return 0
+
+    def xm_bn_ema(self, rm, rv, stats, n_outer, outer_stride, n_inner, inner_stride, C, momentum, stream):
+        self.launches += 1
+        m, v = view(rm, (C,)), view(rv, (C,))
+        for o in range(n_outer):
+            for i in range(n_inner):
+                s = view(stats + 4 * (o * outer_stride + i * inner_stride), (2, C))
+                m.copy_((1 - momentum) * m + momentum * s[0])
+                v.copy_((1 - momentum) * v + momentum * s[1])
+        return 0
