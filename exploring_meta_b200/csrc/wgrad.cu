@@ -1,0 +1,268 @@
+// wgrad.cu -- xm_wgrad: per-task conv weight gradient with the fused SGD / outer-recursion epilogue.
+//
+// GEMM view per task: gW[k = (tap, ci)][co] = sum over pixels of x[pixel + tap][ci] * g[pixel][co];
+// M = 9*cin rows, N = cout, reduction over the n*hz*wz pixels of the task (44,100 at the Mini-ImageNet
+// 42x42 layer).  A CTA owns (task, 32-channel cin chunk, 32-wide cout slice, pixel split): it walks
+// over its share of the pixel tiles (same 128-pixel tiles + halo staging as xm_conv), keeps the whole
+// [<=288][32] accumulator block in registers across tiles (18 m-tiles x 4 n-tiles spread over 4 warps),
+// and writes one partial block at the end.  A second kernel reduces the pixel splits in double and
+// applies the axpy epilogue out = base + scale * gW directly in PyTorch's [co][ci][3][3] layout --
+// this is where theta' = theta - lr*g (learn2learn maml_update, core_functions/vision.py:13) is fused.
+// Contraction: mma.sync m16n8k8 TF32, 3-term error-compensated split (fp32-level accuracy).
+#include "tile.cuh"
+
+namespace xm {
+
+extern int g_precise;
+
+constexpr int WG_THREADS = 128;
+constexpr int GSTR = 40;     // smem row stride of the g tile (32 + 8)
+constexpr int MAXMT = 5;     // m-tiles per warp: ceil(18 / 4)
+
+struct WgradK {
+  TileGeo t;
+  int tasks, cout, cin;
+  int nchunks, npairs, splits;
+  int krows;                   // 9*min(cin,32) rounded up to 16
+  const float* x[2];
+  const float* g[2];
+  float* partial;              // [task][split][9*cin][cout]
+};
+
+template <int PRECISE>
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_kernel(const WgradK p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TileGeo& tg = p.t;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int task = blockIdx.y, split = blockIdx.x;
+  const int cotile = blockIdx.z / p.nchunks, chunk = blockIdx.z - cotile * p.nchunks;
+  const int co0 = cotile * 32, ncols = min(32, p.cout - co0);
+  const int c0 = chunk * 32, cc = min(32, p.cin - c0);
+  const int TW = 1 << tg.tw_log, TH = 1 << tg.th_log;
+  const int halo_px = (1 << tg.ti_log) * tg.halo_h * tg.halo_w;
+  const int n_mt = (9 * cc + 15) >> 4;
+  const bool split_pixels = n_mt < 4;      // few K rows (cin 1..5): warps split the pixels instead
+
+  float* halo = reinterpret_cast<float*>(smem_raw);                 // [halo_px][cstride]
+  float* gs = halo + (size_t)halo_px * tg.cstride;                  // [128][GSTR]
+  int* offtab = reinterpret_cast<int*>(gs + 128 * GSTR);            // [krows]
+  int* pbtab = offtab + p.krows;                                    // [128]
+
+  build_offtab(tg, offtab, p.krows, cc, tid, WG_THREADS);
+  for (int i = tid; i < 128; i += WG_THREADS) pbtab[i] = pixel_base(tg, i);
+  __syncthreads();
+
+  // m-tiles of this warp and the (tile-invariant) halo offsets of its two A rows per m-tile
+  int my_mt[MAXMT], offA[MAXMT][2];
+  int n_my = 0;
+#pragma unroll
+  for (int i = 0; i < MAXMT; ++i) {
+    const int mt = split_pixels ? i : warp + 4 * i;
+    my_mt[i] = mt;
+    if (mt < n_mt) n_my = i + 1;
+    offA[i][0] = offtab[min(mt * 16 + g, p.krows - 1)];
+    offA[i][1] = offtab[min(mt * 16 + g + 8, p.krows - 1)];
+  }
+
+  float acc[MAXMT][4][4];
+#pragma unroll
+  for (int a = 0; a < MAXMT; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  for (int tile = split; tile < tg.tiles_per_task; tile += p.splits) {
+    int i0, h0, w0;
+    tile_origin(tg, tile, i0, h0, w0);
+    for (int pair = 0; pair < p.npairs; ++pair) {
+      __syncthreads();
+      stage_halo(tg, p.x[pair], task, i0, h0, w0, c0, cc, halo, tid, WG_THREADS);
+      // g tile: [128 pixels][ncols], zero for pixels outside the task's grid
+      const float* G = p.g[pair] + (long long)task * tg.n * tg.oh * tg.ow * p.cout;
+      for (int i = tid; i < 128 * 32; i += WG_THREADS) {
+        const int px = i >> 5, col = i & 31;
+        const int pw = px & (TW - 1), ph = (px >> tg.tw_log) & (TH - 1), ti = px >> (tg.tw_log + tg.th_log);
+        const int img = i0 + ti, h = h0 + ph, w = w0 + pw;
+        float v = 0.f;
+        if (col < ncols && img < tg.n && h < tg.oh && w < tg.ow)
+          v = __ldg(G + (((long long)img * tg.oh + h) * tg.ow + w) * p.cout + co0 + col);
+        gs[px * GSTR + col] = v;
+      }
+      __syncthreads();
+
+      const int ks_begin = split_pixels ? warp * 4 : 0, ks_end = split_pixels ? warp * 4 + 4 : 16;
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        const int p0 = ks * 8;
+        const int pb0 = pbtab[p0 + t], pb1 = pbtab[p0 + t + 4];
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float b0 = gs[(p0 + t) * GSTR + nt * 8 + g], b1 = gs[(p0 + t + 4) * GSTR + nt * 8 + g];
+          if (PRECISE) { split_tf32(b0, bh[nt][0], bl[nt][0]); split_tf32(b1, bh[nt][1], bl[nt][1]); }
+          else { bh[nt][0] = f2tf32(b0); bh[nt][1] = f2tf32(b1); }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXMT; ++i) {
+          if (i < n_my) {
+            uint32_t ah[4], al[4];
+            const float a0 = halo[pb0 + offA[i][0]], a1 = halo[pb0 + offA[i][1]];
+            const float a2 = halo[pb1 + offA[i][0]], a3 = halo[pb1 + offA[i][1]];
+            if (PRECISE) {
+              split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+              split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+            } else {
+              ah[0] = f2tf32(a0); ah[1] = f2tf32(a1); ah[2] = f2tf32(a2); ah[3] = f2tf32(a3);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              if (nt * 8 < ncols) {
+                if (PRECISE) {
+                  mma_tf32(acc[i][nt], al, bh[nt]);
+                  mma_tf32(acc[i][nt], ah, bl[nt]);
+                }
+                mma_tf32(acc[i][nt], ah, bh[nt]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- write the partial block: rows k = tap*cc + cl -> global row tap*cin + c0 + cl ---------------
+  float* P = p.partial + ((long long)task * p.splits + split) * 9 * p.cin * p.cout;
+  if (split_pixels) {
+    // cross-warp reduction through shared memory (reuse the staging area)
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem_raw);    // [4 warps][n_mt*16][32]
+#pragma unroll
+    for (int i = 0; i < MAXMT; ++i)
+      if (i < n_my)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = my_mt[i] * 16 + g + (r >> 1) * 8, col = nt * 8 + 2 * t + (r & 1);
+            red[(warp * n_mt * 16 + row) * 32 + col] = acc[i][nt][r];
+          }
+    __syncthreads();
+    for (int i = tid; i < 9 * cc * 32; i += WG_THREADS) {
+      const int row = i >> 5, col = i & 31;
+      if (col < ncols) {
+        float v = 0.f;
+        for (int w = 0; w < 4; ++w) v += red[(w * n_mt * 16 + row) * 32 + col];
+        const int tap = row / cc, cl = row - tap * cc;
+        P[(long long)(tap * p.cin + c0 + cl) * p.cout + co0 + col] = v;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAXMT; ++i)
+      if (i < n_my)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = my_mt[i] * 16 + g + (r >> 1) * 8, col = nt * 8 + 2 * t + (r & 1);
+            if (row < 9 * cc && col < ncols) {
+              const int tap = row / cc, cl = row - tap * cc;
+              P[(long long)(tap * p.cin + c0 + cl) * p.cout + co0 + col] = acc[i][nt][r];
+            }
+          }
+  }
+}
+
+// out_w[task][co][ci][tap] = base_w + scale * sum_split partial[task][split][tap*cin+ci][co]  (double sum)
+// out_b[task][co] = base_b (the conv-bias gradient is analytically zero under train-mode BN).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
+                                    float* out_w, float* out_b, long long out_stride,
+                                    const float* base_w, const float* base_b, long long base_stride,
+                                    float scale) {
+  const int task = blockIdx.y;
+  const int per = 9 * cin * cout;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < per) {
+    const int row = i / cout, co = i - row * cout;
+    const int tap = row / cin, ci = row - tap * cin;
+    const float* P = partial + (long long)task * splits * per + i;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += (double)P[(long long)k * per];
+    const long long o = ((long long)co * cin + ci) * 9 + tap;
+    const float b = base_w ? base_w[(long long)task * base_stride + o] : 0.f;
+    out_w[(long long)task * out_stride + o] = b + scale * (float)s;
+  }
+  if (out_b && i < cout)
+    out_b[(long long)task * out_stride + i] = base_b ? base_b[(long long)task * base_stride + i] : 0.f;
+}
+
+static void wgrad_geo(const XmBlockGeom& g, TileGeo& t) {
+  t = TileGeo{};
+  t.n = g.n; t.oh = g.hz; t.ow = g.wz; t.sh = g.hin; t.sw = g.win; t.sc = g.cin;
+  t.s_eff = g.stride; t.dilate = 1;
+  finish_tile_geo(t, 8);
+}
+
+static int wgrad_splits(const XmBlockGeom& g, const TileGeo& t) {
+  const int per_task_ctas = ((g.cout + 31) / 32) * ((g.cin + 31) / 32);
+  int s = (num_sms() * 3 + g.tasks * per_task_ctas - 1) / (g.tasks * per_task_ctas);
+  if (s > t.tiles_per_task) s = t.tiles_per_task;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" int64_t xm_wgrad_scratch_bytes(const XmBlockGeom* g) {
+  if (!g || !geom_ok(*g)) return -1;
+  TileGeo t;
+  wgrad_geo(*g, t);
+  return (int64_t)g->tasks * wgrad_splits(*g, t) * 9 * g->cin * g->cout * (int64_t)sizeof(float);
+}
+
+extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XM_REQUIRE(a != nullptr, "xm_wgrad: null args");
+  const XmBlockGeom& g = a->g;
+  XM_REQUIRE(geom_ok(g), "xm_wgrad: inconsistent block geometry");
+  XM_REQUIRE(a->x1 && a->g1 && a->out_w && a->partial, "xm_wgrad: null x1/g1/out_w/partial");
+  XM_REQUIRE((a->x2 == nullptr) == (a->g2 == nullptr), "xm_wgrad: x2/g2 must both be given");
+  XM_REQUIRE(!a->src_nchw || (a->row_step > 0 && a->row0 >= 0 &&
+             a->row0 + (long long)(g.n - 1) * a->row_step < a->rows_per_task), "xm_wgrad: bad image row selection");
+  XM_REQUIRE(!(a->src_nchw && a->x2), "xm_wgrad: image sources carry no tangent (x2 must be NULL)");
+  WgradK p{};
+  wgrad_geo(g, p.t);
+  p.t.src_nchw = a->src_nchw; p.t.row0 = a->row0; p.t.row_step = a->row_step; p.t.rows_per_task = a->rows_per_task;
+  p.tasks = g.tasks; p.cout = g.cout; p.cin = g.cin;
+  p.nchunks = (g.cin + 31) / 32;
+  p.npairs = a->x2 ? 2 : 1;
+  p.splits = wgrad_splits(g, p.t);
+  const int ccmax = g.cin < 32 ? g.cin : 32;
+  p.krows = (9 * ccmax + 15) & ~15;
+  p.x[0] = a->x1; p.g[0] = a->g1; p.x[1] = a->x2; p.g[1] = a->g2;
+  p.partial = a->partial;
+  const int64_t need = (int64_t)g.tasks * p.splits * 9 * g.cin * g.cout * 4;
+  XM_REQUIRE(a->partial_bytes >= need, "xm_wgrad: partial buffer too small (%lld < %lld)",
+             (long long)a->partial_bytes, (long long)need);
+  size_t smem = (size_t)halo_pixels(p.t) * p.t.cstride * 4 + 128 * GSTR * 4 + (size_t)(p.krows + 128) * 4;
+  const size_t red = (size_t)4 * p.krows * 32 * 4;       // cross-warp reduction area (small-cin mode)
+  if (p.krows < 64 && smem < red) smem = red;
+  XM_REQUIRE(smem <= 227 * 1024, "xm_wgrad: %zu bytes of shared memory needed", smem);
+  dim3 grid(p.splits, g.tasks, ((g.cout + 31) / 32) * p.nchunks);
+  auto kern = g_precise ? wgrad_kernel<1> : wgrad_kernel<0>;
+  XM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  kern<<<grid, WG_THREADS, smem, stream>>>(p);
+  int rc = launched("xm_wgrad");
+  if (rc) return rc;
+  const int per = 9 * g.cin * g.cout;
+  dim3 rgrid((per + 255) / 256, g.tasks);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, p.splits, g.cin, g.cout, a->out_w, a->out_b,
+                                                a->out_task_stride, a->base_w, a->base_b, a->base_task_stride,
+                                                a->scale);
+  return launched("xm_wgrad(reduce)");
+}

@@ -195,6 +195,11 @@ int xm_bn_ema(float* running_mean, float* running_var, const float* call_stats, 
               int64_t outer_stride, int32_t n_inner, int64_t inner_stride, int32_t channels,
               float momentum, void* stream);
 
+/* Contraction precision of xm_conv / xm_wgrad: 1 (default) = error-compensated 3xTF32 (fp32-level
+ * accuracy, what the parity contract is stated in); 0 = single-pass TF32 (faster, ~1e-3 relative error
+ * per contraction).  Process-wide; set before building / capturing a launch program. */
+int xm_set_precision(int precise);
+
 int xm_version(void);
 const char* xm_last_error(void);
 /* Number of kernel launches this library has issued from the calling process (bench.py's gpu_launches). */
