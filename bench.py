@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- meta-train tasks/sec of the MAML hot path (BASELINE.json configs[1]):
+MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, meta-batch 32 per GPU.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (N>1: launched under torchrun)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+
+One "step" = one meta-iteration over one synthetic meta-batch: adapt T steps on the support rows of every
+task, query loss, second-order meta-gradient, (allreduce), grad/B, Adam.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WAYS, SHOTS, STEPS, INNER_LR, OUTER_LR, TASKS = 5, 5, 5, 0.5, 0.003, 32
+METRIC = 'meta-train tasks/sec (MAML MiniImageNet 5w5s)'
+WORKLOAD = ('MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, '
+            'meta-batch 32 per GPU (synthetic 84x84x3)')
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--tasks', type=int, default=TASKS, help='meta-batch per GPU (default: the named config)')
+    ap.add_argument('--inner-steps', type=int, default=STEPS)
+    ap.add_argument('--fast-tf32', action='store_true', help='single-pass TF32 contractions (not parity-grade)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-breakdown', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'tensor_tflops': d['bf16_tflops_sustained'], 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tensor_tflops': 1400.0, 'source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(tasks, reps, inner_steps):
+    """The reference's CPU path (oracle port: reference model + fast_adapt semantics + learn2learn
+    restatement, fp32, torch intra-op threads = all host cores), train tasks only incl. second-order
+    backward; returns tasks/s over `reps` timed repetitions of a `tasks`-task sample after one warm-up task."""
+    import torch
+    from oracle import maml_oracle as mo
+    from exploring_meta_b200.synthetic import make_tasks
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ospec = mo.miniimagenet_spec(WAYS)
+    params = mo.init_params(ospec, seed=42)
+    X, Y = make_tasks(tasks, WAYS, SHOTS, (3, 84, 84), seed=0)
+    mo.meta_iteration(params, X[:1], Y[:1], ospec, inner_steps, INNER_LR)     # warm-up
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = mo.meta_iteration(params, X, Y, ospec, inner_steps, INNER_LR)
+        state = mo.new_adam_state(params)
+        mo.adam_step(params, [g / tasks for g in out['grad']], state, lr=OUTER_LR)
+        times.append(time.perf_counter() - t0)
+    return tasks / (sum(times) / len(times)), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample_tasks = 2
+    times_all = []
+    for _ in range(args.warmup):
+        pass        # the warm-up task inside cpu_reference_rate covers lazy initialisation
+    rate, cores, times = cpu_reference_rate(sample_tasks, max(1, args.steps), args.inner_steps)
+    times_all += times
+    ms = 1000.0 * sum(times_all) / len(times_all)
+    sample = '%d-task sample of the 32-task meta-batch per step, fp32, %d torch threads' % (sample_tasks, cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'tasks/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'inner_steps': args.inner_steps, 'sample': sample},
+        'cpu_baseline': {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'tasks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def kernel_breakdown(engine, reps=2):
+    """Per-entry-point device time of one launch program, CUDA events on the launching stream around
+    every C-ABI call (un-captured replay).  Returns {name: {'ms': per-step ms, 'calls': n}}."""
+    import ctypes
+    import torch
+    from exploring_meta_b200 import _lib
+    stream = torch.cuda.current_stream()
+    calls = engine.prog.calls
+    totals = {}
+    for rep in range(reps + 1):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in calls]
+        for (fn, cargs, name), (e0, e1) in zip(calls, evs):
+            e0.record(stream)
+            code = fn(*cargs, stream.cuda_stream) if isinstance(cargs, tuple) else fn(ctypes.byref(cargs), stream.cuda_stream)
+            _lib.check(code, name)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if rep == 0:
+            continue
+        for idx, ((fn, cargs, name), (e0, e1)) in enumerate(zip(calls, evs)):
+            d = totals.setdefault(name, {'ms': 0.0, 'calls': 0, 'per_call': {}})
+            ms = e0.elapsed_time(e1)
+            d['ms'] += ms / reps
+            d['calls'] += 1 if rep == 1 else 0
+            d['per_call'][idx] = d['per_call'].get(idx, 0.0) + ms / reps
+    return totals
+
+
+def program_work(engine):
+    """Algorithmic work per entry point of one launch program: conv/wgrad FLOPs (2/MAC)
+    and compulsory bytes of the streaming BN kernels (each tensor touched once)."""
+    from exploring_meta_b200 import _lib
+    work = {}
+    for idx, (fn, a, name) in enumerate(engine.prog.calls):
+        w = work.setdefault(name, {'flops': 0.0, 'bytes': 0.0, 'per_call': {}})
+        if name in ('xm_conv', 'xm_wgrad'):
+            g = a.g
+            pairs = 2 if (getattr(a, 'src2', None) or getattr(a, 'x2', None)) else 1
+            fl = 2.0 * g.tasks * g.n * g.hz * g.wz * 9 * g.cin * g.cout * pairs
+            w['flops'] += fl
+            w['per_call'][idx] = fl
+        elif name.startswith('xm_bn'):
+            g = a.g
+            z = 4.0 * g.tasks * g.n * g.hz * g.wz * g.cout
+            p = 4.0 * g.tasks * g.n * g.hp * g.wp * g.cout
+            by = {'xm_bn_fwd': z + p, 'xm_bn_bwd': 2 * z + p, 'xm_bn_dual_fwd': 2 * z + p,
+                  'xm_bn_dual_bwd': 4 * z + 2 * p}[name]
+            w['bytes'] += by
+            w['per_call'][idx] = by
+    return work
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from exploring_meta_b200 import _lib
+    from exploring_meta_b200 import spec as pspec
+    from exploring_meta_b200.synthetic import make_tasks
+    from exploring_meta_b200.trainer import MamlTrainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: exploring_meta_b200 has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    lib.xm_set_precision(0 if args.fast_tf32 else 1)
+
+    spec = pspec.miniimagenet_spec(WAYS)
+    T = args.inner_steps
+    tr = MamlTrainer(spec, args.tasks, SHOTS, T, INNER_LR, OUTER_LR, device=dev, use_graph=True)
+    tr.theta.copy_(pspec.init_flat_params(spec, seed=42))
+    # two synthetic meta-batches per rank in pinned host memory (seed = data 0 + rank*1000 + batch)
+    host = []
+    for b in range(2):
+        X, Y = make_tasks(args.tasks, WAYS, SHOTS, (3, 84, 84), seed=rank * 1000 + b)
+        host.append((X.pin_memory(), Y.pin_memory()))
+    e = tr.engine
+    e.x.copy_(host[0][0]); e.y.copy_(host[0][1])
+    l0 = int(lib.xm_launch_count())
+    e.prog.replay(torch.cuda.current_stream().cuda_stream)          # eager replay: counts kernels per step
+    torch.cuda.synchronize()
+    kernels_per_step = int(lib.xm_launch_count()) - l0 + 1          # + Adam
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        # inputs already in HBM (engine.x / engine.y): launch program (graph) + reduce + Adam
+        if tr.use_graph:
+            e.capture()
+        e.launch()
+        tr.flat[e.P] = e.loss.sum()
+        tr.flat[e.P + 1] = e.correct.sum()
+        tr._reduce_and_step(tr.theta, tr.tasks * tr.world)
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        resident_step()
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API: pinned host batch in, loss/accuracy out, every step -------
+    for i in range(2):
+        loss, correct = tr.meta_step(*host[i % 2])
+        loss.cpu()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss, correct = tr.meta_step(*host[i % 2])
+        loss_h, correct_h = loss.cpu(), correct.cpu()
+    ev1.record()
+    barrier()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item())
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+    d2h = args.tasks * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    global_tasks = args.tasks * world
+    value = global_tasks * args.steps / (total_ms / 1000.0)
+    e2e = global_tasks * args.steps / (e2e_ms / 1000.0)
+    peaks = measured_peaks()
+    flops_per_task = spec.flops_per_train_task(SHOTS, T)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'tasks/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (tensor-core contractions: %s)' % ('1xTF32' if args.fast_tf32 else '3xTF32 error-compensated, fp32 accumulate'),
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'tasks_per_gpu': args.tasks, 'global_meta_batch': global_tasks,
+                   'inner_steps': T, 'inner_lr': INNER_LR, 'ways': WAYS, 'shots': SHOTS,
+                   'parallelism': 'tasks sharded over %d GPU(s), one fp32 allreduce of %d floats per step' % (world, e.P + 2),
+                   'l2_policy': 'inputs (135.5 MB/step) and activations (several GB/step) exceed the 126 MB L2; no explicit flush',
+                   'cuda_graph': bool(tr.use_graph)},
+        'e2e': {'value': e2e, 'unit': 'tasks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': kernels_per_step * args.steps,
+        'clocks': clocks,
+        'algorithmic_tflops': value * flops_per_task / 1e12,
+        'flops_per_task': flops_per_task,
+    }
+
+    if world == 1 and not args.no_kernel_breakdown:
+        times = kernel_breakdown(e)
+        work = program_work(e)
+        step_ms = sum(v['ms'] for v in times.values())
+        fams = {}
+        for name, tv in sorted(times.items(), key=lambda kv: -kv[1]['ms']):
+            w = work.get(name, {'flops': 0.0, 'bytes': 0.0})
+            fam = {'ms_per_step': round(tv['ms'], 3), 'calls': tv['calls'], 'share': round(tv['ms'] / step_ms, 4)}
+            if w['flops']:
+                fam['tflops'] = round(w['flops'] / tv['ms'] / 1e9, 2)
+            if w['bytes']:
+                fam['gbs'] = round(w['bytes'] / tv['ms'] / 1e6, 1)
+            fams[name] = fam
+        line['kernels'] = fams
+        top = max(times.items(), key=lambda kv: kv[1]['ms'])[0]
+        tv, w = times[top], work.get(top, {'flops': 0.0, 'bytes': 0.0})
+        if w['flops']:
+            achieved = w['flops'] / tv['ms'] / 1e9
+            line['roofline'] = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_tflops'],
+                                'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': None,
+                                'peak_source': peaks['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json); '
+                                'the kernel runs fp32-grade 3xTF32 on mma.sync, so its own ceiling is far lower',
+                                'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
+        else:
+            achieved = w['bytes'] / tv['ms'] / 1e6
+            line['roofline'] = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
+                                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                                'peak_source': peaks['source'], 'launches_per_step': tv['calls'],
+                                'avg_launch_ms': tv['ms'] / tv['calls']}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, times = cpu_reference_rate(2, 2, T)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port',
+                                'sample': '2-task sample x 2 repetitions after a 1-task warm-up, fp32, '
+                                          '%d torch threads (oracle port of the reference path)' % cores}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

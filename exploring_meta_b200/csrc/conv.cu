@@ -30,6 +30,7 @@ struct ConvK {
   int wmode;                       // 0: forward weights, 1: data-gradient (transposed, flipped taps)
   int wt_cin, wt_cout;             // PyTorch weight tensor [wt_cout][wt_cin][3][3]
   int nchunks, npairs, kseg;
+  int resident;                    // 1: all K rows of the weights stay in shared memory for the CTA's lifetime
   int stat_mode;
   const float* src[2];
   const float* w[2];
@@ -53,20 +54,16 @@ conv_kernel(const ConvK p) {
   const int TW = 1 << tg.tw_log, TH = 1 << tg.th_log;
   const int halo_px = (1 << tg.ti_log) * tg.halo_h * tg.halo_w;
 
-  float* ws = reinterpret_cast<float*>(smem_raw);                 // [nseg*kseg][WSTR]
-  float* halo = ws + (size_t)nseg * p.kseg * WSTR;                // [halo_px][cstride]
+  double* sstat = reinterpret_cast<double*>(smem_raw);            // [2][32]
+  float* ws = reinterpret_cast<float*>(sstat + 64);               // [nseg*kseg][WSTR]
+  float* halo = ws + (size_t)(p.resident ? nseg : 1) * p.kseg * WSTR;   // [halo_px][cstride]  (16B aligned)
   int* offtab = reinterpret_cast<int*>(halo + (size_t)halo_px * tg.cstride);  // [kseg]
-  double* sstat = reinterpret_cast<double*>(offtab + p.kseg + (p.kseg & 1));  // [2][32]
 
-  // ---- resident weights: ws[(seg, tap, cl)][co] ---------------------------------------------------
-  for (int i = tid; i < nseg * p.kseg * WSTR; i += CONV_THREADS) ws[i] = 0.f;
-  if (tid < 64) sstat[tid] = 0.0;
-  __syncthreads();
-  for (int seg = 0; seg < nseg; ++seg) {
+  // ---- weights: ws[(seg, tap, cl)][co], transposed from PyTorch's [co][ci][3][3] -----------------
+  auto load_weights = [&](int seg, float* wseg) {
     const int pair = seg / p.nchunks, chunk = seg - pair * p.nchunks;
     const int c0 = chunk * 32, cc = min(32, tg.sc - c0);
     const float* W = p.w[pair] + (long long)task * p.wstride[pair];
-    float* wseg = ws + (size_t)seg * p.kseg * WSTR;
     if (p.wmode == 0) {
       // forward: source channel = conv cin, output channel = conv cout
       const int per_co = cc * 9;
@@ -85,7 +82,12 @@ conv_kernel(const ConvK p) {
             __ldg(W + ((long long)(c0 + cl) * p.wt_cin + co0 + col) * 9 + tap);
       }
     }
-  }
+  };
+  for (int i = tid; i < (p.resident ? nseg : 1) * p.kseg * WSTR; i += CONV_THREADS) ws[i] = 0.f;
+  if (tid < 64) sstat[tid] = 0.0;
+  __syncthreads();
+  if (p.resident)
+    for (int seg = 0; seg < nseg; ++seg) load_weights(seg, ws + (size_t)seg * p.kseg * WSTR);
 
   double st[4][2][2];
 #pragma unroll
@@ -124,45 +126,72 @@ conv_kernel(const ConvK p) {
         last_cc = cc;
       }
       stage_halo(tg, p.src[pair], task, i0, h0, w0, c0, cc, halo, tid, CONV_THREADS);
+      if (!p.resident) {                     // weights streamed per segment (very wide layers only)
+        if (cc < 32) {
+          for (int i = tid; i < p.kseg * WSTR; i += CONV_THREADS) ws[i] = 0.f;
+          __syncthreads();
+        }
+        load_weights(seg, ws);
+      }
       __syncthreads();
 
       // ---- tensor-core contraction over this segment's K rows -----------------------------------
-      const float* wseg = ws + (size_t)seg * p.kseg * WSTR;
+      // The tensor core adds into its fp32 accumulator with truncation, so a long chain of MMAs into
+      // one accumulator drifts (~1e-7 * chain length, biased).  Chains are therefore kept to one
+      // 32-row K chunk (4 k-steps, small correction terms first) in `cacc`, which is then folded into
+      // the running sum `acc` with ordinary round-to-nearest fp32 adds.
+      const float* wseg = p.resident ? ws + (size_t)seg * p.kseg * WSTR : ws;
       const int ksteps = (9 * cc + 7) >> 3;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int k0 = ks * 8;
-        const int o0 = offtab[k0 + t], o1 = offtab[k0 + t + 4];
-        uint32_t ah[2][4], al[2][4];
+      for (int kc = 0; kc < ksteps; kc += 4) {
+        float cacc[2][4][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const float a0 = halo[pbase[mt][0] + o0], a1 = halo[pbase[mt][1] + o0];
-          const float a2 = halo[pbase[mt][0] + o1], a3 = halo[pbase[mt][1] + o1];
-          if (PRECISE) {
-            split_tf32(a0, ah[mt][0], al[mt][0]); split_tf32(a1, ah[mt][1], al[mt][1]);
-            split_tf32(a2, ah[mt][2], al[mt][2]); split_tf32(a3, ah[mt][3], al[mt][3]);
-          } else {
-            ah[mt][0] = f2tf32(a0); ah[mt][1] = f2tf32(a1); ah[mt][2] = f2tf32(a2); ah[mt][3] = f2tf32(a3);
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cacc[a][b][c] = 0.f;
+        const int kend = min(kc + 4, ksteps);
+        for (int ks = kc; ks < kend; ++ks) {
+          const int k0 = ks * 8;
+          const int o0 = offtab[k0 + t], o1 = offtab[k0 + t + 4];
+          uint32_t ah[2][4], al[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const float a0 = halo[pbase[mt][0] + o0], a1 = halo[pbase[mt][1] + o0];
+            const float a2 = halo[pbase[mt][0] + o1], a3 = halo[pbase[mt][1] + o1];
+            if (PRECISE) {
+              split_tf32(a0, ah[mt][0], al[mt][0]); split_tf32(a1, ah[mt][1], al[mt][1]);
+              split_tf32(a2, ah[mt][2], al[mt][2]); split_tf32(a3, ah[mt][3], al[mt][3]);
+            } else {
+              ah[mt][0] = f2tf32(a0); ah[mt][1] = f2tf32(a1); ah[mt][2] = f2tf32(a2); ah[mt][3] = f2tf32(a3);
+            }
           }
-        }
-        const float* wk0 = wseg + (k0 + t) * WSTR + g;
-        const float* wk1 = wk0 + 4 * WSTR;
+          const float* wk0 = wseg + (k0 + t) * WSTR + g;
+          const float* wk1 = wk0 + 4 * WSTR;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          if (nt * 8 < ncols) {
-            uint32_t bh[2], bl[2];
-            const float b0 = wk0[nt * 8], b1 = wk1[nt * 8];
-            if (PRECISE) { split_tf32(b0, bh[0], bl[0]); split_tf32(b1, bh[1], bl[1]); }
-            else { bh[0] = f2tf32(b0); bh[1] = f2tf32(b1); }
+          for (int nt = 0; nt < 4; ++nt) {
+            if (nt * 8 < ncols) {
+              uint32_t bh[2], bl[2];
+              const float b0 = wk0[nt * 8], b1 = wk1[nt * 8];
+              if (PRECISE) { split_tf32(b0, bh[0], bl[0]); split_tf32(b1, bh[1], bl[1]); }
+              else { bh[0] = f2tf32(b0); bh[1] = f2tf32(b1); }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              if (PRECISE) {
-                mma_tf32(acc[mt][nt], al[mt], bh);
-                mma_tf32(acc[mt][nt], ah[mt], bl);
+              for (int mt = 0; mt < 2; ++mt) {
+                if (PRECISE) {
+                  mma_tf32(cacc[mt][nt], al[mt], bh);
+                  mma_tf32(cacc[mt][nt], ah[mt], bl);
+                }
+                mma_tf32(cacc[mt][nt], ah[mt], bh);
               }
-              mma_tf32(acc[mt][nt], ah[mt], bh);
             }
           }
         }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] += cacc[a][b][c];
       }
     }
 
@@ -266,8 +295,13 @@ extern "C" int xm_conv(const XmConvArgs* a, void* stream_) {
   p.out = a->out; p.aux = a->aux; p.stats = a->stats;
 
   const int nseg = p.npairs * p.nchunks;
-  size_t smem = (size_t)nseg * p.kseg * WSTR * 4 + (size_t)halo_pixels(t) * t.cstride * 4 +
-                (size_t)(p.kseg + (p.kseg & 1)) * 4 + 64 * 8 + 16;
+  const size_t fixed = (size_t)halo_pixels(t) * t.cstride * 4 + (size_t)p.kseg * 4 + 64 * 8 + 16;
+  size_t smem = (size_t)nseg * p.kseg * WSTR * 4 + fixed;
+  p.resident = 1;
+  if (smem > 200 * 1024) {
+    p.resident = 0;
+    smem = (size_t)p.kseg * WSTR * 4 + fixed;
+  }
   XM_REQUIRE(smem <= 227 * 1024, "xm_conv: %zu bytes of shared memory needed (cin=%d cout=%d too large)",
              smem, g.cin, g.cout);
   if (p.stat_mode)

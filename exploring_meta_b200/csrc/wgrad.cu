@@ -3,9 +3,9 @@
 // GEMM view per task: gW[k = (tap, ci)][co] = sum over pixels of x[pixel + tap][ci] * g[pixel][co];
 // M = 9*cin rows, N = cout, reduction over the n*hz*wz pixels of the task (44,100 at the Mini-ImageNet
 // 42x42 layer).  A CTA owns (task, 32-channel cin chunk, 32-wide cout slice, pixel split): it walks
-// over its share of the pixel tiles (same 128-pixel tiles + halo staging as xm_conv), keeps the whole
-// [<=288][32] accumulator block in registers across tiles (18 m-tiles x 4 n-tiles spread over 4 warps),
-// and writes one partial block at the end.  A second kernel reduces the pixel splits in double and
+// over its share of the pixel tiles (same 128-pixel tiles + halo staging as xm_conv), accumulates one
+// tile's [<=288][32] block in registers (18 m-tiles x 4 n-tiles spread over 4 warps), folds it into fp32
+// master accumulators in shared memory after every tile, and writes one partial block at the end.  A second kernel reduces the pixel splits in double and
 // applies the axpy epilogue out = base + scale * gW directly in PyTorch's [co][ci][3][3] layout --
 // this is where theta' = theta - lr*g (learn2learn maml_update, core_functions/vision.py:13) is fused.
 // Contraction: mma.sync m16n8k8 TF32, 3-term error-compensated split (fp32-level accuracy).
@@ -24,6 +24,7 @@ struct WgradK {
   int tasks, cout, cin;
   int nchunks, npairs, splits;
   int krows;                   // 9*min(cin,32) rounded up to 16
+  int tab_off;                 // byte offset of the tables / master accumulators behind the staging area
   const float* x[2];
   const float* g[2];
   float* partial;              // [task][split][9*cin][cout]
@@ -47,8 +48,12 @@ wgrad_kernel(const WgradK p) {
 
   float* halo = reinterpret_cast<float*>(smem_raw);                 // [halo_px][cstride]
   float* gs = halo + (size_t)halo_px * tg.cstride;                  // [128][GSTR]
-  int* offtab = reinterpret_cast<int*>(gs + 128 * GSTR);            // [krows]
+  int* offtab = reinterpret_cast<int*>(smem_raw + p.tab_off);       // [krows]
   int* pbtab = offtab + p.krows;                                    // [128]
+  // fp32 master accumulators [MAXMT*16 slots][128 threads]: the tensor core adds into its accumulator
+  // with truncation, so register accumulators only ever hold ONE tile's contribution (48 chained MMAs)
+  // and are folded into these with round-to-nearest adds after every tile.
+  float* macc = reinterpret_cast<float*>(pbtab + 128);              // [MAXMT*16][WG_THREADS]
 
   build_offtab(tg, offtab, p.krows, cc, tid, WG_THREADS);
   for (int i = tid; i < 128; i += WG_THREADS) pbtab[i] = pixel_base(tg, i);
@@ -66,17 +71,18 @@ wgrad_kernel(const WgradK p) {
     offA[i][1] = offtab[min(mt * 16 + g + 8, p.krows - 1)];
   }
 
-  float acc[MAXMT][4][4];
-#pragma unroll
-  for (int a = 0; a < MAXMT; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  for (int i = 0; i < MAXMT * 16; ++i) macc[i * WG_THREADS + tid] = 0.f;
 
   for (int tile = split; tile < tg.tiles_per_task; tile += p.splits) {
     int i0, h0, w0;
     tile_origin(tg, tile, i0, h0, w0);
+    float acc[MAXMT][4][4];
+#pragma unroll
+    for (int a = 0; a < MAXMT; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
     for (int pair = 0; pair < p.npairs; ++pair) {
       __syncthreads();
       stage_halo(tg, p.x[pair], task, i0, h0, w0, c0, cc, halo, tid, WG_THREADS);
@@ -130,6 +136,13 @@ wgrad_kernel(const WgradK p) {
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < MAXMT; ++i)
+      if (i < n_my)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) macc[((i * 4 + nt) * 4 + r) * WG_THREADS + tid] += acc[i][nt][r];
   }
 
   // ---- write the partial block: rows k = tap*cc + cl -> global row tap*cin + c0 + cl ---------------
@@ -146,7 +159,7 @@ wgrad_kernel(const WgradK p) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int row = my_mt[i] * 16 + g + (r >> 1) * 8, col = nt * 8 + 2 * t + (r & 1);
-            red[(warp * n_mt * 16 + row) * 32 + col] = acc[i][nt][r];
+            red[(warp * n_mt * 16 + row) * 32 + col] = macc[((i * 4 + nt) * 4 + r) * WG_THREADS + tid];
           }
     __syncthreads();
     for (int i = tid; i < 9 * cc * 32; i += WG_THREADS) {
@@ -169,7 +182,7 @@ wgrad_kernel(const WgradK p) {
             const int row = my_mt[i] * 16 + g + (r >> 1) * 8, col = nt * 8 + 2 * t + (r & 1);
             if (row < 9 * cc && col < ncols) {
               const int tap = row / cc, cl = row - tap * cc;
-              P[(long long)(tap * p.cin + c0 + cl) * p.cout + co0 + col] = acc[i][nt][r];
+              P[(long long)(tap * p.cin + c0 + cl) * p.cout + co0 + col] = macc[((i * 4 + nt) * 4 + r) * WG_THREADS + tid];
             }
           }
   }
@@ -249,9 +262,12 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
   const int64_t need = (int64_t)g.tasks * p.splits * 9 * g.cin * g.cout * 4;
   XM_REQUIRE(a->partial_bytes >= need, "xm_wgrad: partial buffer too small (%lld < %lld)",
              (long long)a->partial_bytes, (long long)need);
-  size_t smem = (size_t)halo_pixels(p.t) * p.t.cstride * 4 + 128 * GSTR * 4 + (size_t)(p.krows + 128) * 4;
+  size_t stage = (size_t)halo_pixels(p.t) * p.t.cstride * 4 + 128 * GSTR * 4;
   const size_t red = (size_t)4 * p.krows * 32 * 4;       // cross-warp reduction area (small-cin mode)
-  if (p.krows < 64 && smem < red) smem = red;
+  if (p.krows < 64 && stage < red) stage = red;
+  stage = (stage + 15) & ~(size_t)15;
+  p.tab_off = (int)stage;
+  size_t smem = stage + (size_t)(p.krows + 128) * 4 + (size_t)MAXMT * 16 * WG_THREADS * 4;
   XM_REQUIRE(smem <= 227 * 1024, "xm_wgrad: %zu bytes of shared memory needed", smem);
   dim3 grid(p.splits, g.tasks, ((g.cout + 31) / 32) * p.nchunks);
   auto kern = g_precise ? wgrad_kernel<1> : wgrad_kernel<0>;

@@ -191,6 +191,13 @@ class _EngineBase:
     def launches_per_run(self):
         return len(self.prog.calls)
 
+    def rebuild(self):
+        """Re-records the launch program (after a caller re-pointed ``theta`` / ``grad`` at its own
+        buffers) and drops any captured graph."""
+        self.prog = _Program(self.lib)
+        self._graph = None
+        self._build()
+
 
 class MamlEngine(_EngineBase):
     """Meta-gradient of ``tasks`` MAML tasks (second-order by default), all buffers static.

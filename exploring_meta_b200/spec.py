@@ -93,3 +93,33 @@ def anil_body_spec(dataset, ways=5):
     if dataset == 'omni':
         return NetSpec(1, 28, 28, 32, ways, 4, False, 'none')
     return NetSpec(3, 84, 84, 64, ways, 4, True, 'none')
+
+
+def init_flat_params(spec, seed=42):
+    """Flat fp32 parameter vector initialised like the reference constructors under
+    ``torch.manual_seed(seed)`` (``vision/maml_vision.py:57,73``): per block BatchNorm2d with
+    ``uniform_(weight)`` (vision_models.py:175), Conv2d default init then Xavier-uniform / zero bias
+    (:186, :204-207); then the head -- Xavier/zero for MiniImagenetCNN (:103-104), ``normal_()`` weight and
+    zero bias for OmniglotCNN (:47-49).  Same RNG consumption order as the reference, so the same seed
+    gives the same parameters."""
+    import torch
+    torch.manual_seed(seed)
+    parts, cin = [], spec.in_c
+    for _ in range(spec.layers):
+        bn = torch.nn.BatchNorm2d(spec.hidden, affine=True)
+        torch.nn.init.uniform_(bn.weight)
+        conv = torch.nn.Conv2d(cin, spec.hidden, (3, 3), stride=1 if spec.pool else 2, padding=1, bias=True)
+        torch.nn.init.xavier_uniform_(conv.weight.data, gain=1.0)
+        torch.nn.init.constant_(conv.bias.data, 0.0)
+        parts += [bn.weight, bn.bias, conv.weight, conv.bias]
+        cin = spec.hidden
+    if spec.head != 'none':
+        lin = torch.nn.Linear(spec.feat_dim(), spec.ways, bias=True)
+        if spec.head == 'flatten':
+            torch.nn.init.xavier_uniform_(lin.weight.data, gain=1.0)
+            torch.nn.init.constant_(lin.bias.data, 0.0)
+        else:
+            lin.weight.data.normal_()
+            lin.bias.data.mul_(0.0)
+        parts += [lin.weight, lin.bias]
+    return torch.cat([p.detach().reshape(-1).float() for p in parts])

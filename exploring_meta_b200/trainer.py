@@ -1,0 +1,131 @@
+"""Task-batched meta-training step: the body of the reference's outer loop as one call.
+
+``MamlTrainer.meta_step(x, y)`` replaces ``vision/maml_vision.py:95-141`` minus the validation pass:
+``opt.zero_grad()``; for every task ``maml.clone()`` -> ``fast_adapt`` -> ``eval_loss.backward()``;
+``p.grad *= 1/meta_batch_size``; ``Adam.step()``.  The per-task Python loop becomes one replay of a
+captured launch program over the rank's shard of tasks; with ``world_size > 1`` the shard gradients
+are combined by ONE sum-allreduce of the flat fp32 buffer [meta-grad ; loss sum ; correct count]
+(NCCL over NVLink) before the identical, replicated Adam step.  Nothing here synchronises the host.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import AnilEngine, MamlEngine, _p
+
+ADAM_BETAS = (0.9, 0.999)
+ADAM_EPS = 1e-8
+
+
+class _TrainerBase:
+    def _init_common(self, device, outer_lr, total_params, use_graph):
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self.outer_lr = float(outer_lr)
+        self.iteration = 0
+        self.use_graph = bool(use_graph)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # flat fp32 buffer that is all-reduced: [grad (total_params) ; loss sum ; correct count]
+        self.flat = torch.zeros(total_params + 2, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros(total_params, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros(total_params, dtype=torch.float32, device=self.device)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
+
+    def _reduce_and_step(self, theta_all, global_tasks):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.iteration += 1
+        n = theta_all.numel()
+        _lib.check(self.lib.xm_adam_step(_p(theta_all), _p(self.flat), _p(self.m), _p(self.v), n,
+                                         1.0 / global_tasks, self.outer_lr, ADAM_BETAS[0], ADAM_BETAS[1],
+                                         ADAM_EPS, self.iteration, self._stream()), 'xm_adam_step')
+
+
+class MamlTrainer(_TrainerBase):
+    """MAML meta-training over a shard of ``tasks`` tasks per rank.
+
+    ``theta`` [P] holds the master parameters in ``module.parameters()`` order; it is updated in place
+    by every ``meta_step``.  ``metrics()`` returns (mean query loss, mean query accuracy) over the
+    global meta-batch of the last step as device scalars."""
+
+    def __init__(self, spec, tasks, shots, steps, inner_lr, outer_lr=0.003, first_order=False,
+                 device='cuda', use_graph=True):
+        self.engine = MamlEngine(spec, tasks, shots, steps, inner_lr,
+                                 mode='first' if first_order else 'second', device=device)
+        self.spec, self.tasks = spec, int(tasks)
+        self._init_common(device, outer_lr, self.engine.P, use_graph)
+        self.theta = self.engine.theta
+        self.running_mean = [torch.zeros(spec.hidden, device=self.device) for _ in range(spec.layers)]
+        self.running_var = [torch.ones(spec.hidden, device=self.device) for _ in range(spec.layers)]
+        self.num_batches_tracked = 0
+        # the engine accumulates straight into the all-reduce buffer
+        self.engine.grad = self.flat[:self.engine.P]
+        self.engine.rebuild()
+
+    def load_parameters(self, params):
+        """params: iterable of tensors in ``parameters()`` order (e.g. a reference ``MiniImagenetCNN``)."""
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+        assert flat.numel() == self.engine.P
+        self.theta.copy_(flat)
+
+    def meta_step(self, x, y, track_running_stats=True):
+        e = self.engine
+        e.x.copy_(x, non_blocking=True)
+        e.y.copy_(y, non_blocking=True)
+        if self.use_graph and self.device.type == 'cuda':
+            e.capture()
+        e.launch()
+        P = e.P
+        self.flat[P] = e.loss.sum()
+        self.flat[P + 1] = e.correct.sum()
+        if track_running_stats and self.world == 1:
+            self.num_batches_tracked += e.update_running_stats(self.running_mean, self.running_var)
+        self._reduce_and_step(self.theta, self.tasks * self.world)
+        return e.loss, e.correct
+
+    def metrics(self):
+        P, n = self.engine.P, self.tasks * self.world
+        return self.flat[P] / n, self.flat[P + 1] / (n * self.engine.S)
+
+
+class AnilTrainer(_TrainerBase):
+    """ANIL meta-training (``vision/anil_vision.py:109-151``): body + head trained by one Adam over
+    ``list(features.parameters()) + list(head.parameters())`` (:98-99)."""
+
+    def __init__(self, spec, tasks, shots, steps, inner_lr, outer_lr=0.003, first_order=False,
+                 device='cuda', use_graph=True):
+        self.engine = AnilEngine(spec, tasks, shots, steps, inner_lr, first_order=first_order, device=device)
+        self.spec, self.tasks = spec, int(tasks)
+        e = self.engine
+        self._init_common(device, outer_lr, e.P + e.PH, use_graph)
+        # body and head parameters live in one flat vector so that one Adam launch updates both
+        self.theta_all = torch.zeros(e.P + e.PH, dtype=torch.float32, device=self.device)
+        e.theta = self.theta_all[:e.P]
+        e.head = self.theta_all[e.P:]
+        e.grad = self.flat[:e.P]
+        e.head_grad = self.flat[e.P:e.P + e.PH]
+        e.rebuild()
+
+    def load_parameters(self, body_params, head_params):
+        flat = torch.cat([p.detach().reshape(-1).float() for p in list(body_params) + list(head_params)])
+        assert flat.numel() == self.theta_all.numel()
+        self.theta_all.copy_(flat)
+
+    def meta_step(self, x, y):
+        e = self.engine
+        e.x.copy_(x, non_blocking=True)
+        e.y.copy_(y, non_blocking=True)
+        if self.use_graph and self.device.type == 'cuda':
+            e.capture()
+        e.launch()
+        n = e.P + e.PH
+        self.flat[n] = e.loss.sum()
+        self.flat[n + 1] = e.correct.sum()
+        self._reduce_and_step(self.theta_all, self.tasks * self.world)
+        return e.loss, e.correct
+
+    def metrics(self):
+        n, g = self.engine.P + self.engine.PH, self.tasks * self.world
+        return self.flat[n] / g, self.flat[n + 1] / (g * self.engine.S)
