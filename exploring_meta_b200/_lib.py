@@ -95,6 +95,7 @@ SYMBOLS = {
     'xm_bn_ema': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int32,
                             c_float, c_void_p]),
     'xm_set_precision': (c_int32, [c_int32]),
+    'xm_set_tcgen05': (c_int32, [c_int32]),
     'xm_version': (c_int32, []),
     'xm_last_error': (ctypes.c_char_p, []),
     'xm_launch_count': (c_int64, []),

@@ -199,6 +199,9 @@ int xm_bn_ema(float* running_mean, float* running_var, const float* call_stats, 
  * accuracy, what the parity contract is stated in); 0 = single-pass TF32 (faster, ~1e-3 relative error
  * per contraction).  Process-wide; set before building / capturing a launch program. */
 int xm_set_precision(int precise);
+/* 1 (default): 32-channel stride-1 convolutions run on the tcgen05 / TMEM kernel; 0: every shape uses the
+ * generic mma.sync kernel (A/B comparison and fallback). */
+int xm_set_tcgen05(int enable);
 
 int xm_version(void);
 const char* xm_last_error(void);

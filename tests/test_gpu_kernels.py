@@ -66,6 +66,10 @@ CONV_CASES = [
     (2, 5, 64, 64, 14, 2, False),    # Omniglot stride-2 layer
     (1, 9, 64, 64, 4, 2, False),     # tiny maps: several images per tile
     (2, 2, 8, 12, 9, 1, True),       # unusual channel counts
+    (2, 3, 32, 32, 42, 1, True),     # tcgen05 path: one tile per CTA
+    (40, 3, 32, 32, 42, 1, True),    # tcgen05 path: ~15 tiles per CTA (pipeline phases wrap)
+    (3, 25, 32, 32, 10, 1, True),    # tcgen05 path: small maps, many images per tile
+    (2, 6, 32, 32, 5, 1, True),
 ]
 
 
