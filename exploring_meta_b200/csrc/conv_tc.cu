@@ -22,17 +22,18 @@
 // therefore uses FOUR TMEM accumulators -- one per kernel row kh for the hi*hi terms (12 MMAs each) and one for
 // all small correction terms -- which the epilogue sums with round-to-nearest adds.
 //
-// Pipeline (warp-specialised, 1 CTA per SM, 160 threads): warps 0-3 stage tile i+1 (global -> split -> smem)
-// and run the epilogue of tile i (tcgen05.ld -> NHWC store + BatchNorm statistics); lane 0 of warp 4 issues
-// the MMAs of tile i+1 meanwhile.  Two shared-memory stages and two TMEM accumulator sets, mbarrier
+// Pipeline (warp-specialised, 1 CTA per SM, 288 threads): warps 0-7 stage tile i+1 (global -> split -> smem)
+// and run the epilogue of tile i (tcgen05.ld -> NHWC store + BatchNorm statistics; warp w reads TMEM lane
+// quarter w%4, column half w/4); lane 0 of warp 8 issues the MMAs of tile i+1 meanwhile.  Two shared-memory stages and two TMEM accumulator sets, mbarrier
 // full/free handshakes, tcgen05.commit for completion.
-#include "common.cuh"
+#include "tc.cuh"
 
 namespace xm {
 
-constexpr int TC_THREADS = 160;
-constexpr int TC_WORKERS = 128;
+constexpr int TC_WORKERS = 256;       // 8 producer / epilogue warps
+constexpr int TC_THREADS = TC_WORKERS + 32;   // + the MMA-issuing warp
 constexpr int TC_TMEM_COLS = 256;     // 2 stages x 4 accumulators x 32 columns
+constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 32, 0, 0);   // A and B K-major
 
 struct ConvTcK {
   int tasks, n, H, W, Hp, Wp;        // source == output spatial dims (stride 1)
@@ -44,69 +45,6 @@ struct ConvTcK {
   const float* src; const float* w; long long wstride;
   float* out; const float* aux; double* stats;
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, canonical K-major layout without swizzle:
-// element (row, k) at start + (row/8)*SBO + (row%8)*16 + (k/4)*LBO + (k%4)*4 bytes.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  return d;                                     // base_offset = 0, layout_type = SWIZZLE_NONE
-}
-
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 32
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ---- kernel ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
@@ -132,7 +70,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == TC_WORKERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -161,37 +99,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   const int ntiles = (p.tiles_per_task - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // my tiles
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp < 4) {
+  if (warp < TC_WORKERS / 32) {
     // =============================== producer + epilogue warps ======================================
-    const int c4 = tid & 7, jrow = tid >> 3;
+    const int c4 = tid & 7, jrow = tid >> 3;                   // staging: channel group, first row (0..31)
+    const int quarter = warp & 3, half = warp >> 2;            // epilogue: TMEM lane quarter, column half
     const float* S = p.src + (long long)task * p.n * p.H * p.W * 32;
-    float ssum[32], ssq[32];
+    float ssum[16], ssq[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.f;
+    for (int c = 0; c < 16; ++c) ssum[c] = ssq[c] = 0.f;
 
     auto stage = [&](int it) {
       const int s = it & 1;
       const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
       unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)c4 * plane;
       unsigned char* lo = hi + set_bytes;
-      const int qb = q0 - p.Wp - 1;
-      for (int j0 = jrow; j0 < p.R; j0 += 64) {
+      // position of this thread's first row, then advanced incrementally by 32 positions per row step
+      int q = q0 - p.Wp - 1 + jrow;
+      int img, r, c;
+      if (q >= 0) { img = q / HpWp; const int rem = q - img * HpWp; r = rem / p.Wp; c = rem - r * p.Wp; }
+      else { img = -1; r = p.Hp - 1; c = q + p.Wp; if (c < 0) { c += p.Wp; r -= 1; } }   // rows before the task start: q >= -Wp-1
+      for (int j0 = jrow; j0 < p.R; j0 += 128) {
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 16 * u;
+          const int j = j0 + 32 * u;
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int q = qb + j;
-          if (j < p.R && q >= 0 && q < p.Q) {
-            const int img = q / HpWp, rem = q - img * HpWp;
-            const int r = rem / p.Wp, c = rem - r * p.Wp;
-            if (r >= 1 && c < p.W)
-              v[u] = __ldg(reinterpret_cast<const float4*>(S + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
-          }
+          if (j < p.R && img >= 0 && img < p.n && r >= 1 && c < p.W)
+            v[u] = __ldg(reinterpret_cast<const float4*>(S + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
+          c += 32;
+          while (c >= p.Wp) { c -= p.Wp; r += 1; }
+          while (r >= p.Hp) { r -= p.Hp; img += 1; }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 16 * u;
+          const int j = j0 + 32 * u;
           if (j < p.R) {
             float4 h, l;
             h.x = __uint_as_float(f2tf32(v[u].x)); l.x = v[u].x - h.x;
@@ -217,42 +158,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       }
       mbar_wait(bar_tfull + 8 * s, (it >> 1) & 1);
       tc_fence_after();
-      // ---- epilogue: row (32*warp + lane) of the tile --------------------------------------------------
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 128);
-      float v[32], t[32];
-      tmem_ld32(taddr + 96, v);                      // correction terms
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        tmem_ld32(taddr + 32 * a, t);                // hi*hi terms of kernel row a
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] += t[c];
-      }
+      // ---- epilogue: row (32*quarter + lane) of the tile, columns [16*half, 16*half+16) -----------------
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128 + half * 16);
+      uint32_t r0[16], r1[16], r2[16], r3[16];
+      tmem_ld16_nowait(taddr + 96, r3);              // correction terms
+      tmem_ld16_nowait(taddr, r0);                   // hi*hi terms of kernel rows 0..2
+      tmem_ld16_nowait(taddr + 32, r1);
+      tmem_ld16_nowait(taddr + 64, r2);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_tfree + 8 * s);                // TMEM set s may be overwritten
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        v[k] = ((__uint_as_float(r3[k]) + __uint_as_float(r0[k])) + __uint_as_float(r1[k])) + __uint_as_float(r2[k]);
 
-      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + warp * 32 + lane;
+      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + quarter * 32 + lane;
       if (q < p.Q) {
         const int img = q / HpWp, rem = q - img * HpWp;
         const int r = rem / p.Wp, c = rem - r * p.Wp;
         if (r >= 1 && c < p.W) {
-          const long long o = ((((long long)task * p.n + img) * p.H + (r - 1)) * p.W + c) * 32;
+          const long long o = ((((long long)task * p.n + img) * p.H + (r - 1)) * p.W + c) * 32 + half * 16;
           float4* dst = reinterpret_cast<float4*>(p.out + o);
           if (p.accumulate) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               const float4 old = dst[k];
               v[4 * k] += old.x; v[4 * k + 1] += old.y; v[4 * k + 2] += old.z; v[4 * k + 3] += old.w;
             }
           }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           if (p.stat_mode == XM_STAT_SUM_SQ) {
 #pragma unroll
-            for (int c2 = 0; c2 < 32; ++c2) { ssum[c2] += v[c2]; ssq[c2] = fmaf(v[c2], v[c2], ssq[c2]); }
+            for (int c2 = 0; c2 < 16; ++c2) { ssum[c2] += v[c2]; ssq[c2] = fmaf(v[c2], v[c2], ssq[c2]); }
           } else if (p.stat_mode == XM_STAT_SUM_AUX) {
             const float4* ax = reinterpret_cast<const float4*>(p.aux + o);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               const float4 a4 = __ldg(ax + k);
               ssum[4 * k] += v[4 * k]; ssum[4 * k + 1] += v[4 * k + 1];
               ssum[4 * k + 2] += v[4 * k + 2]; ssum[4 * k + 3] += v[4 * k + 3];
@@ -264,14 +207,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       }
     }
     if (p.stat_mode) {
-      // per-thread fp32 partials (<= a few hundred terms each) -> double across the CTA -> global atomics
+      // per-thread fp32 partials (<= a few hundred terms each) -> double across the warp -> global atomics
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 16; ++c) {
         const double a = warp_sum((double)ssum[c]);
         const double b = warp_sum((double)ssq[c]);
         if (lane == 0) {
-          atomicAdd(&p.stats[((long long)task * 2) * 32 + c], a);
-          atomicAdd(&p.stats[((long long)task * 2 + 1) * 32 + c], b);
+          atomicAdd(&p.stats[((long long)task * 2) * 32 + half * 16 + c], a);
+          atomicAdd(&p.stats[((long long)task * 2 + 1) * 32 + half * 16 + c], b);
         }
       }
     }
@@ -299,9 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
               const uint64_t bh = umma_desc(b_hi + bo, 512u, 128u);
               const uint64_t bl = umma_desc(b_lo + bo, 512u, 128u);
               const uint32_t first_corr = (kh | kw | ks) != 0;
-              umma_tf32(d0 + 96, al, bh, first_corr);
-              umma_tf32(d0 + 96, ah, bl, 1u);
-              umma_tf32(d0 + 32 * kh, ah, bh, (uint32_t)((kw | ks) != 0));
+              umma_tf32(d0 + 96, al, bh, TC_IDESC, first_corr);
+              umma_tf32(d0 + 96, ah, bl, TC_IDESC, 1u);
+              umma_tf32(d0 + 32 * kh, ah, bh, TC_IDESC, (uint32_t)((kw | ks) != 0));
             }
           }
         }
@@ -314,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_WORKERS / 32) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }

@@ -14,6 +14,9 @@
 namespace xm {
 
 extern int g_precise;
+extern int g_use_tc;
+int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out);
+long long wgrad_tc_partial_floats(const XmBlockGeom& g);
 
 constexpr int WG_THREADS = 128;
 constexpr int GSTR = 40;     // smem row stride of the g tile (32 + 8)
@@ -235,7 +238,10 @@ extern "C" int64_t xm_wgrad_scratch_bytes(const XmBlockGeom* g) {
   if (!g || !geom_ok(*g)) return -1;
   TileGeo t;
   wgrad_geo(*g, t);
-  return (int64_t)g->tasks * wgrad_splits(*g, t) * 9 * g->cin * g->cout * (int64_t)sizeof(float);
+  int64_t floats = (int64_t)g->tasks * wgrad_splits(*g, t) * 9 * g->cin * g->cout;
+  const int64_t tc = wgrad_tc_partial_floats(*g);
+  if (tc > floats) floats = tc;
+  return floats * (int64_t)sizeof(float);
 }
 
 extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
@@ -248,6 +254,21 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
   XM_REQUIRE(!a->src_nchw || (a->row_step > 0 && a->row0 >= 0 &&
              a->row0 + (long long)(g.n - 1) * a->row_step < a->rows_per_task), "xm_wgrad: bad image row selection");
   XM_REQUIRE(!(a->src_nchw && a->x2), "xm_wgrad: image sources carry no tangent (x2 must be NULL)");
+  if (g_use_tc && g_precise) {
+    // 32-channel stride-1 layers run on the tcgen05 / TMEM kernel (wgrad_tc.cu)
+    XM_REQUIRE(a->partial_bytes >= wgrad_tc_partial_floats(g) * 4, "xm_wgrad: partial buffer too small");
+    int rc = 0;
+    const int tsplits = wgrad_tc_try(a, stream, &rc);
+    if (tsplits < 0) return rc;
+    if (tsplits > 0) {
+      const int per = 9 * g.cin * g.cout;
+      dim3 rgrid((per + 255) / 256, g.tasks);
+      wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, tsplits, g.cin, g.cout, a->out_w, a->out_b,
+                                                    a->out_task_stride, a->base_w, a->base_b,
+                                                    a->base_task_stride, a->scale);
+      return launched("xm_wgrad(reduce)");
+    }
+  }
   WgradK p{};
   wgrad_geo(g, p.t);
   p.t.src_nchw = a->src_nchw; p.t.row0 = a->row0; p.t.row_step = a->row_step; p.t.rows_per_task = a->rows_per_task;

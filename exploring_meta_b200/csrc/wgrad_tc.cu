@@ -1,0 +1,288 @@
+// wgrad_tc.cu -- tcgen05 / TMEM implementation of xm_wgrad for the 32-channel stride-1 layers.
+//
+// gW[tap][ci][co] = sum over positions q of g[q][co] * x[q + delta_tap][ci], on the same flattened
+// padded position sequence as conv_tc.cu (g is staged as zero at padding positions).  The reduction
+// dimension of the GEMM is the POSITION axis, so both operands are MN-major: position rows of 128 B
+// (= the 32 channels of one position, i.e. the natural NHWC row) in the 128B-swizzle/32B-base layout,
+//     A = G^T : M = cout, K = 8 consecutive position rows
+//     B = X   : N = cin,  K = 8 position rows starting at row  k0 + kh*Wp + kw  (the tap is a whole-row shift
+//               of the descriptor start address; the swizzle is a function of absolute address bits)
+// One tcgen05.mma (kind::tf32, M=128, N=32, K=8) per tap, k-step and expansion term.  Only 32 accumulator
+// rows are needed (M = 32 does not exist): LBO = 0 makes the four 32-row groups of A alias the same data, so
+// all four TMEM lane quarters hold the same [32 x 32] result and the four epilogue warps share the nine tap
+// accumulators without any steering.  Accumulators are drained after every tile into fp32 registers with
+// round-to-nearest adds (the tensor core's own accumulation truncates), and each CTA writes one partial
+// block per task split; wgrad_reduce_kernel (wgrad.cu) reduces the splits in double and applies the fused
+// SGD / outer-recursion epilogue.
+#include "tc.cuh"
+
+namespace xm {
+
+constexpr int WT_WORKERS = 256;
+constexpr int WT_THREADS = WT_WORKERS + 32;
+constexpr int WT_TMEM_COLS = 512;            // 9 accumulators x 32 columns (288) -> next power of two
+constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 32, 1, 1);   // A and B MN-major
+
+struct WgradTcK {
+  int tasks, n, H, W, Hp, Wp, Q;
+  int tiles_per_task, splits, npairs;
+  int R, xbuf;                        // staged x rows per tile, bytes of one x buffer (hi or lo)
+  int off_x0, off_x1, off_g0, off_g1, off_bar;   // shared-memory byte offsets
+  const float* x[2];
+  const float* g[2];
+  float* partial;                     // [task][split][9*32][32]
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int task = blockIdx.y, split = blockIdx.x;
+  const int xset = p.xbuf;
+  constexpr int gset = 128 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
+                 bar_tfree = smem_u32(bars + 5);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, WT_WORKERS);
+      mbar_init(bar_sfree + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfree, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WT_WORKERS / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(WT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ntiles = (p.tiles_per_task - split + p.splits - 1) / p.splits;
+  const int nunits = ntiles * p.npairs;
+  const int HpWp = p.Hp * p.Wp;
+
+  if (warp < WT_WORKERS / 32) {
+    // =============================== producers (+ warps 0-3: accumulator drain) =========================
+    const int c4 = tid & 7, jrow = tid >> 3;
+    float macc[3][32];                      // fp32 master accumulators: taps warp, warp+4, warp+8
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 32; ++c) macc[a][c] = 0.f;
+
+    auto split_store = [](const float4& v, unsigned char* hi, unsigned char* lo) {
+      float4 h, l;
+      h.x = __uint_as_float(f2tf32(v.x)); l.x = v.x - h.x;
+      h.y = __uint_as_float(f2tf32(v.y)); l.y = v.y - h.y;
+      h.z = __uint_as_float(f2tf32(v.z)); l.z = v.z - h.z;
+      h.w = __uint_as_float(f2tf32(v.w)); l.w = v.w - h.w;
+      *reinterpret_cast<float4*>(hi) = h;
+      *reinterpret_cast<float4*>(lo) = l;
+    };
+
+    auto stage = [&](int u) {
+      const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
+      const int q0 = (split + it * p.splits) * 128;
+      const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * 32;
+      const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * 32;
+      // ---- x halo: rows j <-> positions q0 - Wp - 1 + j ------------------------------------------------
+      {
+        unsigned char* hi = smem + (s ? p.off_x1 : p.off_x0) + (c4 & 1) * 16;
+        unsigned char* lo = hi + xset;
+        const int ch = c4 >> 1;               // 32 B chunk of the 128 B row; swizzled with the row index
+        int q = q0 - p.Wp - 1 + jrow;
+        int img, r, c;
+        if (q >= 0) { img = q / HpWp; const int rem = q - img * HpWp; r = rem / p.Wp; c = rem - r * p.Wp; }
+        else { img = -1; r = p.Hp - 1; c = q + p.Wp; if (c < 0) { c += p.Wp; r -= 1; } }
+        for (int j0 = jrow; j0 < p.R; j0 += 128) {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = j0 + 32 * k;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < p.R && img >= 0 && img < p.n && r >= 1 && c < p.W)
+              v[k] = __ldg(reinterpret_cast<const float4*>(X + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
+            c += 32;
+            while (c >= p.Wp) { c -= p.Wp; r += 1; }
+            while (r >= p.Hp) { r -= p.Hp; img += 1; }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = j0 + 32 * k;
+            if (j < p.R) {
+              const size_t o = (size_t)j * 128 + (size_t)((ch ^ (j & 3)) * 32);
+              split_store(v[k], hi + o, lo + o);
+            }
+          }
+        }
+      }
+      // ---- g tile: rows i <-> positions q0 + i, zero at padding positions ----------------------------------
+      {
+        unsigned char* hi = smem + (s ? p.off_g1 : p.off_g0) + (c4 & 1) * 16;
+        unsigned char* lo = hi + gset;
+        const int ch = c4 >> 1;
+        int q = q0 + jrow;
+        int img = q / HpWp;
+        const int rem = q - img * HpWp;
+        int r = rem / p.Wp, c = rem - r * p.Wp;
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (img < p.n && r >= 1 && c < p.W)
+            v[k] = __ldg(reinterpret_cast<const float4*>(G + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
+          c += 32;
+          while (c >= p.Wp) { c -= p.Wp; r += 1; }
+          while (r >= p.Hp) { r -= p.Hp; img += 1; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = jrow + 32 * k;
+          const size_t o = (size_t)i * 128 + (size_t)((ch ^ (i & 3)) * 32);
+          split_store(v[k], hi + o, lo + o);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    };
+
+    if (nunits > 0) stage(0);
+    for (int u = 0; u < nunits; ++u) {
+      if (u + 1 < nunits) {
+        if (u >= 1) mbar_wait(bar_sfree + 8 * ((u + 1) & 1), ((u - 1) >> 1) & 1);
+        stage(u + 1);
+      }
+      const int it = u / p.npairs;
+      if (warp < 4 && (u - it * p.npairs) == p.npairs - 1) {
+        // ---- drain the tile's accumulators: lane = cout, 32 cin columns per tap --------------------------
+        mbar_wait(bar_tfull, it & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float v[32];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const int tap = warp + 4 * a;
+          if (tap < 9) {                         // warp-uniform
+            tmem_ld32(taddr + (uint32_t)(tap * 32), v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) macc[a][c] += v[c];
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tfree);
+      }
+    }
+    if (warp < 4) {
+      float* P = p.partial + ((long long)task * p.splits + split) * 9 * 32 * 32;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int tap = warp + 4 * a;
+        if (tap < 9) {
+#pragma unroll
+          for (int ci = 0; ci < 32; ++ci) P[(tap * 32 + ci) * 32 + lane] = macc[a][ci];
+        }
+      }
+    }
+  } else {
+    // ======================================= MMA issuer =================================================
+    for (int u = 0; u < nunits; ++u) {
+      const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
+      mbar_wait(bar_full + 8 * s, (u >> 1) & 1);
+      if (pair == 0 && it >= 1) mbar_wait(bar_tfree, (it - 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t x_hi = smem_u32(smem + (s ? p.off_x1 : p.off_x0)), x_lo = x_hi + (uint32_t)xset;
+        const uint32_t g_hi = smem_u32(smem + (s ? p.off_g1 : p.off_g0)), g_lo = g_hi + (uint32_t)gset;
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint32_t fresh = (pair == 0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t aoff = (uint32_t)(ks * 8) * 128u;
+            const uint32_t boff = (uint32_t)(ks * 8 + kh * p.Wp + kw) * 128u;
+            const uint64_t ah = umma_desc(g_hi + aoff, 0u, 512u, 1u);      // LBO 0: four aliased 32-row groups
+            const uint64_t al = umma_desc(g_lo + aoff, 0u, 512u, 1u);
+            const uint64_t bh = umma_desc(x_hi + boff, 0u, 512u, 1u);
+            const uint64_t bl = umma_desc(x_lo + boff, 0u, 512u, 1u);
+            const uint32_t d = tmem_base + (uint32_t)(tap * 32);
+            umma_tf32(d, al, bh, WT_IDESC, fresh);
+            umma_tf32(d, ah, bl, WT_IDESC, 1u);
+            umma_tf32(d, ah, bh, WT_IDESC, 1u);
+          }
+        }
+        umma_commit(bar_sfree + 8 * s);
+        if (pair == p.npairs - 1) umma_commit(bar_tfull);
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WT_WORKERS / 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WT_TMEM_COLS) : "memory");
+  }
+}
+
+static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
+  if (g.cin != 32 || g.cout != 32 || g.stride != 1) return false;
+  p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
+  p.Q = g.n * p.Hp * p.Wp;
+  p.tiles_per_task = (p.Q + 127) / 128;
+  p.R = 128 + 2 * p.Wp + 2;
+  p.xbuf = ((p.R + 7) & ~7) * 128;                   // whole 1 KB units keep every buffer 1024 B aligned
+  const int gbuf = 128 * 128;
+  p.off_x0 = 0;
+  p.off_g0 = p.off_x0 + 2 * p.xbuf;
+  p.off_x1 = p.off_g0 + 2 * gbuf;
+  p.off_g1 = p.off_x1 + 2 * p.xbuf;
+  p.off_bar = p.off_g1 + 2 * gbuf;
+  smem = (size_t)p.off_bar + 8 * 8 + 16;
+  int splits = num_sms() / g.tasks;
+  if (splits < 1) splits = 1;
+  if (splits > p.tiles_per_task) splits = p.tiles_per_task;
+  p.splits = splits;
+  return smem <= 227 * 1024;
+}
+
+// partial-buffer floats needed by the tcgen05 path for this geometry (0 if the shape is not covered)
+long long wgrad_tc_partial_floats(const XmBlockGeom& g) {
+  WgradTcK p{};
+  size_t smem;
+  if (!wgrad_tc_layout(g, p, smem)) return 0;
+  return (long long)g.tasks * p.splits * 9 * 32 * 32;
+}
+
+// Returns the number of splits written to a->partial (>0) when handled, 0 when not covered, <0 on error.
+int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out) {
+  const XmBlockGeom& g = a->g;
+  *rc_out = 0;
+  if (a->src_nchw) return 0;
+  WgradTcK p{};
+  size_t smem;
+  if (!wgrad_tc_layout(g, p, smem)) return 0;
+  p.tasks = g.tasks;
+  p.npairs = a->x2 ? 2 : 1;
+  p.x[0] = a->x1; p.g[0] = a->g1; p.x[1] = a->x2; p.g[1] = a->g2;
+  p.partial = a->partial;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  dim3 grid(p.splits, g.tasks);
+  wgrad_tc_kernel<<<grid, WT_THREADS, smem, stream>>>(p);
+  if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
+  return p.splits;
+}
+
+}  // namespace xm
