@@ -191,6 +191,100 @@ wgrad_kernel(const WgradK p) {
   }
 }
 
+
+// ---- image layer (cin <= 4, stride 1, NCHW source): CUDA-core kernel ---------------------------------------
+// K = 9*cin <= 36 is far too thin for the tensor pipe and the layer is bound by streaming g (cout floats per
+// pixel) anyway: lane = cout channel, warps split the pixels of a 4-row band whose zero-padded source halo
+// (6 x (W+2) pixels x 4 channels) sits in shared memory; every g element is loaded once (coalesced 128 B per
+// warp) and meets its 27 source values through broadcast 16 B shared loads.
+constexpr int WI_THREADS = 256;
+constexpr int WI_ROWS = 4;
+
+struct WgradImgK {
+  int n, H, W, cin, cout, splits;
+  int row0, row_step, rows_per_task;
+  const float* x; const float* g;
+  float* partial;              // [task][split][9*cin][cout]
+};
+
+__global__ void __launch_bounds__(WI_THREADS)
+wgrad_img_kernel(const WgradImgK p) {
+  extern __shared__ __align__(16) float4 sh4[];                 // [WI_ROWS+2][W+2] pixels (x, y, z, w = channels)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int task = blockIdx.y, split = blockIdx.x, co = blockIdx.z * 32 + lane;
+  const int Wp = p.W + 2;
+  const int bands_per_img = (p.H + WI_ROWS - 1) / WI_ROWS;
+  const int nbands = p.n * bands_per_img;
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+  const float* G = p.g + (long long)task * p.n * p.H * p.W * p.cout;
+
+  for (int band = split; band < nbands; band += p.splits) {
+    const int img = band / bands_per_img, y0 = (band - img * bands_per_img) * WI_ROWS;
+    const float* X = p.x + ((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * p.cin * p.H * p.W;
+    __syncthreads();
+    for (int i = tid; i < (WI_ROWS + 2) * Wp; i += WI_THREADS) {
+      const int yy = i / Wp, xx = i - yy * Wp;
+      const int y = y0 - 1 + yy, x = xx - 1;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < p.cin) v[c] = __ldg(X + ((long long)c * p.H + y) * p.W + x);
+      }
+      sh4[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    const int rows = min(WI_ROWS, p.H - y0);
+    for (int i = warp; i < rows * p.W; i += WI_THREADS / 32) {
+      const int ry = i / p.W, x = i - ry * p.W;
+      float gv = 0.f;
+      if (co < p.cout) gv = __ldg(G + (((long long)img * p.H + y0 + ry) * p.W + x) * p.cout + co);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4 xv = sh4[(ry + kh) * Wp + x + kw];
+          acc[kh * 3 + kw][0] = fmaf(gv, xv.x, acc[kh * 3 + kw][0]);
+          acc[kh * 3 + kw][1] = fmaf(gv, xv.y, acc[kh * 3 + kw][1]);
+          acc[kh * 3 + kw][2] = fmaf(gv, xv.z, acc[kh * 3 + kw][2]);
+          acc[kh * 3 + kw][3] = fmaf(gv, xv.w, acc[kh * 3 + kw][3]);
+        }
+    }
+  }
+  // cross-warp reduction, then one partial block per (task, split)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sh4);                   // [8 warps][36][32]
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[(warp * 36 + t * 4 + c) * 32 + lane] = acc[t][c];
+  __syncthreads();
+  float* P = p.partial + ((long long)task * p.splits + split) * 9 * p.cin * p.cout;
+  for (int i = tid; i < 36 * 32; i += WI_THREADS) {
+    const int slot = i >> 5, l = i & 31, t = slot >> 2, c = slot & 3;
+    const int col = blockIdx.z * 32 + l;
+    if (c < p.cin && col < p.cout) {
+      float v = 0.f;
+      for (int w = 0; w < WI_THREADS / 32; ++w) v += red[(w * 36 + slot) * 32 + l];
+      P[(long long)(t * p.cin + c) * p.cout + col] = v;
+    }
+  }
+}
+
+static int wgrad_img_splits(const XmBlockGeom& g) {
+  const int cotiles = (g.cout + 31) / 32;
+  int s = (num_sms() * 6 + g.tasks * cotiles - 1) / (g.tasks * cotiles);
+  const int nbands = g.n * ((g.hin + WI_ROWS - 1) / WI_ROWS);
+  if (s > nbands) s = nbands;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
 // out_w[task][co][ci][tap] = base_w + scale * sum_split partial[task][split][tap*cin+ci][co]  (double sum)
 // out_b[task][co] = base_b (the conv-bias gradient is analytically zero under train-mode BN).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
@@ -241,6 +335,8 @@ extern "C" int64_t xm_wgrad_scratch_bytes(const XmBlockGeom* g) {
   int64_t floats = (int64_t)g->tasks * wgrad_splits(*g, t) * 9 * g->cin * g->cout;
   const int64_t tc = wgrad_tc_partial_floats(*g);
   if (tc > floats) floats = tc;
+  const int64_t im = (int64_t)g->tasks * wgrad_img_splits(*g) * 9 * g->cin * g->cout;
+  if (g->cin <= 4 && g->stride == 1 && im > floats) floats = im;
   return floats * (int64_t)sizeof(float);
 }
 
@@ -268,6 +364,34 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
                                                     a->base_task_stride, a->scale);
       return launched("xm_wgrad(reduce)");
     }
+  }
+  if (a->src_nchw && g.cin <= 4 && g.stride == 1 && !a->x2) {
+    // image layer: CUDA-core streaming kernel
+    WgradImgK k{};
+    k.n = g.n; k.H = g.hin; k.W = g.win; k.cin = g.cin; k.cout = g.cout;
+    k.splits = wgrad_img_splits(g);
+    k.row0 = a->row0; k.row_step = a->row_step; k.rows_per_task = a->rows_per_task;
+    k.x = a->x1; k.g = a->g1; k.partial = a->partial;
+    XM_REQUIRE(a->partial_bytes >= (int64_t)g.tasks * k.splits * 9 * g.cin * g.cout * 4,
+               "xm_wgrad: partial buffer too small");
+    size_t smem = (size_t)(WI_ROWS + 2) * (g.win + 2) * 16;
+    const size_t red = (size_t)8 * 36 * 32 * 4;
+    if (smem < red) smem = red;
+    XM_REQUIRE(smem <= 200 * 1024, "xm_wgrad: image too wide");
+    static bool attr_set = false;
+    if (!attr_set) {
+      XM_CUDA(cudaFuncSetAttribute(wgrad_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    dim3 grid(k.splits, g.tasks, (g.cout + 31) / 32);
+    wgrad_img_kernel<<<grid, WI_THREADS, smem, stream>>>(k);
+    if (int rc = launched("xm_wgrad(image)")) return rc;
+    const int per = 9 * g.cin * g.cout;
+    dim3 rgrid((per + 255) / 256, g.tasks);
+    wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, k.splits, g.cin, g.cout, a->out_w, a->out_b,
+                                                  a->out_task_stride, a->base_w, a->base_b,
+                                                  a->base_task_stride, a->scale);
+    return launched("xm_wgrad(reduce)");
   }
   WgradK p{};
   wgrad_geo(g, p.t);

@@ -197,24 +197,26 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       mbar_wait(bar_full + 8 * s, (u >> 1) & 1);
       if (pair == 0 && it >= 1) mbar_wait(bar_tfree, (it - 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t x_hi = smem_u32(smem + (s ? p.off_x1 : p.off_x0)), x_lo = x_hi + (uint32_t)xset;
-        const uint32_t g_hi = smem_u32(smem + (s ? p.off_g1 : p.off_g0)), g_lo = g_hi + (uint32_t)gset;
+      if (elect_one_sync()) {
+        // descriptor low words (start address, LBO = 0); per MMA only the start field moves
+        const uint32_t x_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_x1 : p.off_x0)), 0u);
+        const uint32_t x_lo0 = x_hi0 + (uint32_t)(xset >> 4);
+        const uint32_t g_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_g1 : p.off_g0)), 0u);
+        const uint32_t g_lo0 = g_hi0 + (uint32_t)(gset >> 4);
+        constexpr uint32_t dhi = umma_desc_hi(512u, 1u);            // SBO 512 B, 128B-swizzle / 32B-base layout
+        uint32_t tapoff[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 8u;   // rows * 128 B / 16
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t fresh = (pair == 0 && ks == 0) ? 0u : 1u;
+          const uint32_t ko = (uint32_t)ks * 64u;                   // 8 position rows of 128 B per K step
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t aoff = (uint32_t)(ks * 8) * 128u;
-            const uint32_t boff = (uint32_t)(ks * 8 + kh * p.Wp + kw) * 128u;
-            const uint64_t ah = umma_desc(g_hi + aoff, 0u, 512u, 1u);      // LBO 0: four aliased 32-row groups
-            const uint64_t al = umma_desc(g_lo + aoff, 0u, 512u, 1u);
-            const uint64_t bh = umma_desc(x_hi + boff, 0u, 512u, 1u);
-            const uint64_t bl = umma_desc(x_lo + boff, 0u, 512u, 1u);
+            const uint32_t bo = ko + tapoff[tap];
             const uint32_t d = tmem_base + (uint32_t)(tap * 32);
-            umma_tf32(d, al, bh, WT_IDESC, fresh);
-            umma_tf32(d, ah, bl, WT_IDESC, 1u);
-            umma_tf32(d, ah, bh, WT_IDESC, 1u);
+            umma_tf32_lh(d, g_lo0 + ko, dhi, x_hi0 + bo, dhi, WT_IDESC, fresh);
+            umma_tf32_lh(d, g_hi0 + ko, dhi, x_lo0 + bo, dhi, WT_IDESC, 1u);
+            umma_tf32_lh(d, g_hi0 + ko, dhi, x_hi0 + bo, dhi, WT_IDESC, 1u);
           }
         }
         umma_commit(bar_sfree + 8 * s);

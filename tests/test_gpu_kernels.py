@@ -70,6 +70,8 @@ CONV_CASES = [
     (40, 3, 32, 32, 42, 1, True),    # tcgen05 path: ~15 tiles per CTA (pipeline phases wrap)
     (3, 25, 32, 32, 10, 1, True),    # tcgen05 path: small maps, many images per tile
     (2, 6, 32, 32, 5, 1, True),
+    (2, 2, 3, 32, 84, 1, True),      # image layer at full Mini-ImageNet resolution (tcgen05 image variant)
+    (33, 2, 3, 32, 30, 1, True),     # image layer, several tiles per CTA
 ]
 
 
