@@ -88,6 +88,16 @@ def init_params(spec, seed=42, with_head=True, dtype=torch.float32):
     return [p.detach().clone().to(dtype) for p in params]
 
 
+def init_anil_params(spec, seed=42, dtype=torch.float32):
+    """ANIL parameters as ``vision/anil_vision.py:86-94`` creates them under ``torch.manual_seed``: the
+    ``ConvBase`` body (same RNG consumption as the blocks of ``init_params``) and then a default-initialised
+    ``torch.nn.Linear(fc_neurons, ways)`` head.  Returns (body list, head list)."""
+    body = init_params(spec, seed=seed, with_head=False, dtype=dtype)     # leaves the RNG after the blocks
+    h, w = spec.out_hw()
+    lin = torch.nn.Linear(spec.hidden * h * w, spec.ways)
+    return body, [lin.weight.detach().clone().to(dtype), lin.bias.detach().clone().to(dtype)]
+
+
 def body_forward(params, x, spec, bn_log=None):
     """``ConvBase.forward`` = 4x ``ConvBlock.forward`` (vision_models.py:188-193): conv -> BN with
     per-call batch statistics (no .eval() exists anywhere in the reference) -> ReLU -> max-pool."""
