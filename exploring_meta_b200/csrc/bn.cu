@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256) bn_dual_bwd_apply_kernel(const BnK k) {
           o[v] = gr[v] * proj;
           od[v] = coef[v] * proj + gr[v] * (gbnd - e1[v] - xhd * m2[v] - xhat * m2dot[v]);
         }
-        Vec<VEC>::st(k.gz + w.zoff[d], o);
+        if (k.gz) Vec<VEC>::st(k.gz + w.zoff[d], o);
         Vec<VEC>::st(k.gzdot + w.zoff[d], od);
       }
   }
@@ -476,16 +476,17 @@ static int fill(const XmBnArgs* a, BnK& k, bool pooled_grid, int& vec, int& thre
   threads = (256 / cq) * cq;
   const long long items = (long long)g.n * k.wh * k.ww * cq;
   long long want = (items + threads - 1) / threads;
-  long long cap = ((long long)num_sms() * 8 + g.tasks - 1) / g.tasks;
-  if (cap < 1) cap = 1;
-  blocks = (int)(want < cap ? want : cap);
+  blocks = (int)(want < 65535 ? want : 65535);      // BN_LAUNCH clamps to one resident wave of the kernel
   if (blocks < 1) blocks = 1;
   return 1;
 }
 
 #define BN_LAUNCH(kernel, smem)                                                            \
   do {                                                                                     \
-    dim3 grid(blocks, a->g.tasks);                                                         \
+    const void* fn_ = vec == 4 ? (const void*)kernel<4> : (const void*)kernel<1>;          \
+    int cap_ = wave_ctas(fn_, threads, smem) / a->g.tasks;                                 \
+    if (cap_ < 1) cap_ = 1;                                                                \
+    dim3 grid(blocks < cap_ ? blocks : cap_, a->g.tasks);                                  \
     if (vec == 4) kernel<4><<<grid, threads, smem, stream>>>(k);                           \
     else kernel<1><<<grid, threads, smem, stream>>>(k);                                    \
   } while (0)
@@ -547,7 +548,7 @@ extern "C" int xm_bn_dual_fwd(const XmBnArgs* a, void* stream_) {
 extern "C" int xm_bn_dual_bwd(const XmBnArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = bn_common_checks(a, "xm_bn_dual_bwd")) return rc;
-  XM_REQUIRE(a->zdot && a->gp && a->mean_invstd && a->bwd_red && a->dual_red && a->gamma_dot && a->gz &&
+  XM_REQUIRE(a->zdot && a->gp && a->mean_invstd && a->bwd_red && a->dual_red && a->gamma_dot &&
              a->gzdot && a->scratch, "xm_bn_dual_bwd: null zdot/gp/mean_invstd/bwd_red/dual_red/gamma_dot/gz/gzdot/scratch");
   XM_REQUIRE((a->out_gamma == nullptr) == (a->out_beta == nullptr), "xm_bn_dual_bwd: out_gamma/out_beta must both be given");
   BnK k; int vec, threads, blocks;

@@ -43,6 +43,9 @@ inline int geom_ok(const XmBlockGeom& g) {
 }
 
 int num_sms();
+// CTAs of `kernel` (threads per CTA, dynamic shared memory) that are resident on the whole GPU at once (SMs x
+// occupancy): grids are sized to at most this, in one wave -- a grid a few CTAs larger runs a second wave.
+int wave_ctas(const void* kernel, int threads, size_t smem);
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t f2tf32(float x) {
@@ -63,6 +66,14 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = f2tf32(x);
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// Packed fp32 FMA (sm_100 FFMA2): (d0, d1) += a * (b0, b1) with the scalar a broadcast -- one issue slot for two
+// FMAs; the plain 3-register FFMA issues at half rate on Blackwell, so FMA-bound CUDA-core loops use this.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a), "f"(b0), "f"(b1));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -249,6 +249,7 @@ conv_kernel(const ConvK p) {
 int g_precise = 1;
 int g_use_tc = 1;
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream);
+int conv_img_try(const XmConvArgs* a, cudaStream_t stream);
 
 }  // namespace xm
 
@@ -260,7 +261,7 @@ extern "C" int xm_set_precision(int precise) {
 }
 
 extern "C" int xm_set_tcgen05(int enable) {
-  g_use_tc = enable ? 1 : 0;
+  g_use_tc = enable;
   return 0;
 }
 
@@ -279,6 +280,11 @@ extern "C" int xm_conv(const XmConvArgs* a, void* stream_) {
   XM_REQUIRE(!a->src_nchw || (a->row_step > 0 && a->row0 >= 0 &&
              a->row0 + (long long)(g.n - 1) * a->row_step < a->rows_per_task), "xm_conv: bad image row selection");
 
+  if (g_use_tc == 1) {
+    // image layer (cin <= 4, stride 1): exact-fp32 CUDA-core kernel, HBM-write bound (conv_img.cu)
+    const int rc = conv_img_try(a, stream);
+    if (rc != 0) return rc == 1 ? 0 : rc;
+  }
   if (g_use_tc && g_precise) {
     // 32-channel stride-1 layers run on the tcgen05 / TMEM kernel (conv_tc.cu)
     const int rc = conv_tc_try(a, stream);

@@ -101,9 +101,26 @@ struct HeadK {
   float scale;
 };
 
+// Feature rows in their NATIVE order: Xn(i, e) with e = s*c + ch for mode 0 (the NHWC element order, so a warp
+// reads 128 B lines) and e = ch for mode 1 (spatial mean).  The weights are permuted once into shared memory to
+// the same order: Wn[w][e] = W[w][ch*hw + s].
+struct NFeat {
+  const float* f; int hw, c, mode, De;
+  __device__ __forceinline__ float at(int i, int e) const {
+    if (mode == 0) return __ldg(f + (long long)i * De + e);
+    float acc = 0.f;
+    for (int s = 0; s < hw; ++s) acc += __ldg(f + ((long long)i * hw + s) * c + e);
+    return acc / (float)hw;
+  }
+};
+
+// head_kernel: grid (tasks, G).  Every CTA of a task recomputes the (tiny) logits / softmax phase, then the
+// G CTAs split the parameter-gradient and feature-gradient phases over the feature index range -- no
+// inter-CTA synchronisation, G x the parallelism of one CTA per task.
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k) {
   extern __shared__ float sm[];
-  const int task = blockIdx.x, tid = threadIdx.x;
+  const int task = blockIdx.x, part = blockIdx.y, nparts = gridDim.y, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = HEAD_THREADS / 32;
   const int n = k.n, ways = k.ways, D = k.D;
   float* logit = sm;                        // [n][ways]
   float* prob = logit + n * ways;           // [n][ways]
@@ -112,20 +129,58 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k) {
   float* gld = ld + n * ways;               // [n][ways]   tangent of dL/dlogits    (dual)
   float* row_loss = gld + n * ways;         // [n]
   int* row_ok = reinterpret_cast<int*>(row_loss + n);   // [n]
+  float* Wn = row_loss + 2 * n;             // [ways][D]   native order
+  float* Wdn = Wn + ways * D;               // [ways][D]   (dual)
 
   const long long fbase = (long long)task * n * k.hw * k.c;
-  const Feat X{k.feat + fbase, k.hw, k.c, k.mode, 0, 1};
-  const Feat Xd{k.feat_dot ? k.feat_dot + fbase : nullptr, k.hw, k.c, k.mode, 0, 1};
+  const NFeat X{k.feat + fbase, k.hw, k.c, k.mode, D};
+  const NFeat Xd{k.feat_dot ? k.feat_dot + fbase : nullptr, k.hw, k.c, k.mode, D};
+  const bool have_xd = k.dual && k.feat_dot;
   const float* W = k.w + (long long)task * k.wb_stride;
   const float* B = k.b + (long long)task * k.wb_stride;
   const float* Wd = k.dual ? k.w_dot + (long long)task * k.wbdot_stride : nullptr;
   const float* Bd = k.dual ? k.b_dot + (long long)task * k.wbdot_stride : nullptr;
   const int64_t* lab = k.labels + (long long)task * k.labels_per_task;
 
-  logits_pass(X, W, B, nullptr, nullptr, n, ways, D, logit);
-  if (k.dual) {
-    if (k.feat_dot) logits_pass(X, Wd, Bd, &Xd, W, n, ways, D, ld);
-    else logits_pass(X, Wd, Bd, nullptr, nullptr, n, ways, D, ld);
+  // native index e -> PyTorch feature index
+  auto perm = [&](int e) { return k.mode == 0 ? (e % k.c) * k.hw + e / k.c : e; };
+  for (int idx = tid; idx < ways * D; idx += HEAD_THREADS) {
+    const int w = idx / D, e = idx - w * D;
+    Wn[idx] = __ldg(W + (long long)w * D + perm(e));
+    if (k.dual) Wdn[idx] = __ldg(Wd + (long long)w * D + perm(e));
+  }
+  __syncthreads();
+
+  // ---- logits (and their tangent): one warp per row, 8 classes at a time ----------------------------------
+  for (int i = warp; i < n; i += nwarps) {
+    for (int w0 = 0; w0 < ways; w0 += 8) {
+      float acc[8], accd[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = accd[j] = 0.f;
+      for (int e = lane; e < D; e += 32) {
+        const float x = X.at(i, e);
+        const float xd = have_xd ? Xd.at(i, e) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (w0 + j < ways) {
+            const float wv = Wn[(w0 + j) * D + e];
+            acc[j] = fmaf(x, wv, acc[j]);
+            if (k.dual) accd[j] = fmaf(xd, wv, fmaf(x, Wdn[(w0 + j) * D + e], accd[j]));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (w0 + j < ways) {
+          const float a = warp_sum(acc[j]);
+          if (lane == 0) logit[i * ways + w0 + j] = a + B[w0 + j];
+          if (k.dual) {
+            const float ad = warp_sum(accd[j]);
+            if (lane == 0) ld[i * ways + w0 + j] = ad + Bd[w0 + j];
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   softmax_rows(logit, lab, k.label_row0, k.label_row_step, n, ways, prob, row_loss, row_ok);
@@ -141,55 +196,81 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k) {
       if (k.dual) gld[i * ways + w] = p * (ld[i * ways + w] - pd) / (float)n;
     }
   }
-  if (tid == 0) {
-    float s = 0.f;
-    int ok = 0;
-    for (int i = 0; i < n; ++i) { s += row_loss[i]; ok += row_ok[i]; }
-    if (k.loss) k.loss[task] = s / (float)n;
-    if (k.correct) k.correct[task] = ok;
+  if (part == 0) {
+    if (tid == 0) {
+      float s = 0.f;
+      int ok = 0;
+      for (int i = 0; i < n; ++i) { s += row_loss[i]; ok += row_ok[i]; }
+      if (k.loss) k.loss[task] = s / (float)n;
+      if (k.correct) k.correct[task] = ok;
+    }
+    if (k.logits)
+      for (int i = tid; i < n * ways; i += blockDim.x) k.logits[(long long)task * n * ways + i] = logit[i];
   }
-  if (k.logits)
-    for (int i = tid; i < n * ways; i += blockDim.x) k.logits[(long long)task * n * ways + i] = logit[i];
   __syncthreads();
 
-  // ---- parameter gradients through the axpy epilogue -------------------------------------------------
+  // this CTA's slice of the feature index range
+  const int e_lo = (int)((long long)D * part / nparts), e_hi = (int)((long long)D * (part + 1) / nparts);
+  const float* G = k.dual ? gld : gl;
+  // ---- parameter gradients through the axpy epilogue: thread = feature index e, all classes --------------
   if (k.out_w) {
     float* OW = k.out_w + (long long)task * k.out_stride;
     float* OB = k.out_b + (long long)task * k.out_stride;
     const float* BW = k.base_w ? k.base_w + (long long)task * k.base_stride : nullptr;
     const float* BB = k.base_b ? k.base_b + (long long)task * k.base_stride : nullptr;
-    const float* G = k.dual ? gld : gl;
-    for (int idx = tid; idx < ways * D; idx += blockDim.x) {
-      const int w = idx / D, d = idx - w * D;
-      float acc = 0.f;
-      for (int i = 0; i < n; ++i) {
-        acc = fmaf(G[i * ways + w], X.at(i, d), acc);
-        if (k.dual && k.feat_dot) acc = fmaf(gl[i * ways + w], Xd.at(i, d), acc);
+    for (int e = e_lo + tid; e < e_hi; e += HEAD_THREADS) {
+      const int d = perm(e);
+      for (int w0 = 0; w0 < ways; w0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int i = 0; i < n; ++i) {
+          const float x = X.at(i, e);
+          const float xd = have_xd ? Xd.at(i, e) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (w0 + j < ways) {
+              acc[j] = fmaf(G[i * ways + w0 + j], x, acc[j]);
+              if (have_xd) acc[j] = fmaf(gl[i * ways + w0 + j], xd, acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (w0 + j < ways) {
+            const long long idx = (long long)(w0 + j) * D + d;
+            OW[idx] = (BW ? BW[idx] : 0.f) + k.scale * acc[j];
+          }
       }
-      OW[idx] = (BW ? BW[idx] : 0.f) + k.scale * acc;
     }
-    for (int w = tid; w < ways; w += blockDim.x) {
-      float acc = 0.f;
-      for (int i = 0; i < n; ++i) acc += G[i * ways + w];
-      OB[w] = (BB ? BB[w] : 0.f) + k.scale * acc;
-    }
+    if (part == 0)
+      for (int w = tid; w < ways; w += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc += G[i * ways + w];
+        OB[w] = (BB ? BB[w] : 0.f) + k.scale * acc;
+      }
   }
-  // ---- feature gradient ---------------------------------------------------------------------------
+  // ---- feature gradient (native order: coalesced stores) ---------------------------------------------------
   float* GF = k.dual ? k.g_feat_dot : k.g_feat;
   if (GF) {
-    const FeatGrad out{GF + fbase, k.hw, k.c, k.mode, 0, 1};
-    for (int idx = tid; idx < n * D; idx += blockDim.x) {
-      const int i = idx / D, d = idx - i * D;
+    float* out = GF + fbase;
+    const int span = e_hi - e_lo;
+    for (int idx = tid; idx < n * span; idx += HEAD_THREADS) {
+      const int i = idx / span, e = e_lo + idx - i * span;
       float acc = 0.f;
       for (int w = 0; w < ways; ++w) {
         if (k.dual) {
-          acc = fmaf(gld[i * ways + w], W[(long long)w * D + d], acc);
-          acc = fmaf(gl[i * ways + w], Wd[(long long)w * D + d], acc);
+          acc = fmaf(gld[i * ways + w], Wn[w * D + e], acc);
+          acc = fmaf(gl[i * ways + w], Wdn[w * D + e], acc);
         } else {
-          acc = fmaf(gl[i * ways + w], W[(long long)w * D + d], acc);
+          acc = fmaf(gl[i * ways + w], Wn[w * D + e], acc);
         }
       }
-      out.put(i, d, acc, false);
+      if (k.mode == 0) {
+        out[(long long)i * D + e] = acc;
+      } else {
+        const float u = acc / (float)k.hw;
+        for (int s = 0; s < k.hw; ++s) out[((long long)i * k.hw + s) * k.c + e] = u;
+      }
     }
   }
 }
@@ -386,10 +467,14 @@ extern "C" int xm_head(const XmHeadArgs* a, void* stream_) {
   k.out_w = a->out_w; k.out_b = a->out_b; k.out_stride = a->out_task_stride;
   k.base_w = a->base_w; k.base_b = a->base_b; k.base_stride = a->base_task_stride;
   k.scale = a->scale;
-  const size_t smem = ((size_t)5 * a->n * a->ways + 2 * a->n) * 4;
-  XM_REQUIRE(smem <= 200 * 1024, "xm_head: n*ways too large");
+  const size_t smem = ((size_t)5 * a->n * a->ways + 2 * a->n + (size_t)(a->dual ? 2 : 1) * a->ways * k.D) * 4;
+  XM_REQUIRE(smem <= 200 * 1024, "xm_head: n*ways + ways*D too large for shared memory");
   XM_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  head_kernel<<<a->tasks, HEAD_THREADS, smem, stream>>>(k);
+  int parts = (num_sms() + a->tasks - 1) / a->tasks;       // CTAs per task: fill the GPU, at most 8
+  if (parts > 8) parts = 8;
+  if (parts > k.D) parts = k.D;
+  if (parts < 1) parts = 1;
+  head_kernel<<<dim3(a->tasks, parts), HEAD_THREADS, smem, stream>>>(k);
   return launched("xm_head");
 }
 

@@ -16,6 +16,22 @@ int num_sms() {
   return n;
 }
 
+int wave_ctas(const void* kernel, int threads, size_t smem) {
+  struct Entry { const void* k; int threads; size_t smem; int value; };
+  static thread_local Entry cache[32];
+  static thread_local int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == smem) return cache[i].value;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int value = per_sm * num_sms();
+  if (used < 32) cache[used++] = Entry{kernel, threads, smem, value};
+  return value;
+}
+
 // dst[i] = (accumulate ? dst[i] : 0) + sum_t src[t*stride + i], tasks added in index order in fp32
 // (= the order eval_loss.backward() accumulates into the master .grad, vision/maml_vision.py:112).
 __global__ void accumulate_tasks_kernel(const float* __restrict__ src, long long stride, int tasks,

@@ -198,7 +198,8 @@ wgrad_kernel(const WgradK p) {
 // (6 x (W+2) pixels x 4 channels) sits in shared memory; every g element is loaded once (coalesced 128 B per
 // warp) and meets its 27 source values through broadcast 16 B shared loads.
 constexpr int WI_THREADS = 256;
-constexpr int WI_ROWS = 4;
+constexpr int WI_ROWS = 12;
+constexpr int WI_UNROLL = 12;
 
 struct WgradImgK {
   int n, H, W, cin, cout, splits;
@@ -239,20 +240,32 @@ wgrad_img_kernel(const WgradImgK p) {
     }
     __syncthreads();
     const int rows = min(WI_ROWS, p.H - y0);
-    for (int i = warp; i < rows * p.W; i += WI_THREADS / 32) {
-      const int ry = i / p.W, x = i - ry * p.W;
-      float gv = 0.f;
-      if (co < p.cout) gv = __ldg(G + (((long long)img * p.H + y0 + ry) * p.W + x) * p.cout + co);
+    const float* Gb = G + ((long long)img * p.H + y0) * p.W * p.cout + co;
+    // A warp takes WI_UNROLL consecutive pixels of one row per iteration and issues all their loads before the
+    // first FMA, so each warp keeps WI_UNROLL x 128 B in flight (the kernel streams g once and is latency-bound
+    // otherwise).  Packed FFMA2: the g value is the broadcast scalar against channel pairs of the x pixel.
+    const int segs_per_row = (p.W + WI_UNROLL - 1) / WI_UNROLL;
+    for (int seg = warp; seg < rows * segs_per_row; seg += WI_THREADS / 32) {
+      const int ry = seg / segs_per_row, x0 = (seg - ry * segs_per_row) * WI_UNROLL;
+      const float* Gr = Gb + ((long long)ry * p.W + x0) * p.cout;
+      float gv[WI_UNROLL];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int u = 0; u < WI_UNROLL; ++u)
+        gv[u] = (x0 + u < p.W && co < p.cout) ? __ldg(Gr + (long long)u * p.cout) : 0.f;
+      const float4* xrow = sh4 + ry * Wp + x0;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float4 xv = sh4[(ry + kh) * Wp + x + kw];
-          acc[kh * 3 + kw][0] = fmaf(gv, xv.x, acc[kh * 3 + kw][0]);
-          acc[kh * 3 + kw][1] = fmaf(gv, xv.y, acc[kh * 3 + kw][1]);
-          acc[kh * 3 + kw][2] = fmaf(gv, xv.z, acc[kh * 3 + kw][2]);
-          acc[kh * 3 + kw][3] = fmaf(gv, xv.w, acc[kh * 3 + kw][3]);
+      for (int u = 0; u < WI_UNROLL; ++u) {
+        if (x0 + u < p.W) {                           // warp-uniform
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float4 xv = xrow[kh * Wp + u + kw];
+              ffma2(acc[kh * 3 + kw][0], acc[kh * 3 + kw][1], gv[u], xv.x, xv.y);
+              ffma2(acc[kh * 3 + kw][2], acc[kh * 3 + kw][3], gv[u], xv.z, xv.w);
+            }
         }
+      }
     }
   }
   // cross-warp reduction, then one partial block per (task, split)
@@ -275,9 +288,15 @@ wgrad_img_kernel(const WgradImgK p) {
   }
 }
 
+static size_t wgrad_img_smem(const XmBlockGeom& g) {
+  size_t smem = (size_t)(WI_ROWS + 2) * (g.win + 2) * 16;
+  const size_t red = (size_t)8 * 36 * 32 * 4;
+  return smem < red ? red : smem;
+}
+
 static int wgrad_img_splits(const XmBlockGeom& g) {
   const int cotiles = (g.cout + 31) / 32;
-  int s = (num_sms() * 6 + g.tasks * cotiles - 1) / (g.tasks * cotiles);
+  int s = wave_ctas((const void*)wgrad_img_kernel, WI_THREADS, wgrad_img_smem(g)) / (g.tasks * cotiles);   // one wave
   const int nbands = g.n * ((g.hin + WI_ROWS - 1) / WI_ROWS);
   if (s > nbands) s = nbands;
   if (s > 64) s = 64;
@@ -374,9 +393,7 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
     k.x = a->x1; k.g = a->g1; k.partial = a->partial;
     XM_REQUIRE(a->partial_bytes >= (int64_t)g.tasks * k.splits * 9 * g.cin * g.cout * 4,
                "xm_wgrad: partial buffer too small");
-    size_t smem = (size_t)(WI_ROWS + 2) * (g.win + 2) * 16;
-    const size_t red = (size_t)8 * 36 * 32 * 4;
-    if (smem < red) smem = red;
+    const size_t smem = wgrad_img_smem(g);
     XM_REQUIRE(smem <= 200 * 1024, "xm_wgrad: image too wide");
     static bool attr_set = false;
     if (!attr_set) {

@@ -4,23 +4,26 @@
 // padded position sequence as conv_tc.cu (g is staged as zero at padding positions).  The reduction
 // dimension of the GEMM is the POSITION axis, so both operands are MN-major: position rows of 128 B
 // (= the 32 channels of one position, i.e. the natural NHWC row) in the 128B-swizzle/32B-base layout,
-//     A = G^T : M = cout, K = 8 consecutive position rows
-//     B = X   : N = cin,  K = 8 position rows starting at row  k0 + kh*Wp + kw  (the tap is a whole-row shift
-//               of the descriptor start address; the swizzle is a function of absolute address bits)
-// One tcgen05.mma (kind::tf32, M=128, N=32, K=8) per tap, k-step and expansion term.  Only 32 accumulator
-// rows are needed (M = 32 does not exist): LBO = 0 makes the four 32-row groups of A alias the same data, so
-// all four TMEM lane quarters hold the same [32 x 32] result and the four epilogue warps share the nine tap
-// accumulators without any steering.  Accumulators are drained after every tile into fp32 registers with
-// round-to-nearest adds (the tensor core's own accumulation truncates), and each CTA writes one partial
-// block per task split; wgrad_reduce_kernel (wgrad.cu) reduces the splits in double and applies the fused
-// SGD / outer-recursion epilogue.
+// (the swizzle is a function of absolute address bits, so whole-row shifts of a descriptor start address or
+// of LBO address the same swizzled data).  A = X halo (M = 4 shifted copies x cin, K = 8 position rows)
+// and B = G (N = cout, K = 8 consecutive position rows).  The M = 128 rows of one tcgen05.mma (kind::tf32,
+// N = 32, K = 8) are FOUR 32-channel groups whose shared-memory stride is LBO; with LBO = 128 B = one position
+// row, group j is the x halo shifted by j positions -- i.e. the kernel-column taps kw = 0, 1, 2 (group 3 is
+// unused) of one kernel row kh come out of ONE instruction:
+//     D_kh[(kw, ci)][co] += sum_k x[row k0 + k + kh*Wp + kw][ci] * g[row k0 + k][co]
+// so a k-step costs 3 MMAs per expansion term instead of 9.  TMEM lane quarter kw holds tap (kh, kw), lane = ci,
+// column = co.  Two accumulator sets (2 x 3 x 32 columns) let the drain of tile i overlap the MMAs of tile i+1.
+// Accumulators are drained after every tile into fp32 registers with round-to-nearest adds (the tensor
+// core's own accumulation truncates), and each CTA writes one partial block per task split;
+// wgrad_reduce_kernel (wgrad.cu) reduces the splits in double and applies the fused SGD / outer-recursion
+// epilogue.
 #include "tc.cuh"
 
 namespace xm {
 
 constexpr int WT_WORKERS = 256;
 constexpr int WT_THREADS = WT_WORKERS + 32;
-constexpr int WT_TMEM_COLS = 512;            // 9 accumulators x 32 columns (288) -> next power of two
+constexpr int WT_TMEM_COLS = 256;            // 2 sets x 3 accumulators x 32 columns (192) -> next power of two
 constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 32, 1, 1);   // A and B MN-major
 
 struct WgradTcK {
@@ -42,21 +45,32 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
-                 bar_tfree = smem_u32(bars + 5);
+                 bar_tfree = smem_u32(bars + 6);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full + 8 * s, WT_WORKERS);
       mbar_init(bar_sfree + 8 * s, 1);
     }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfree, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tfree + 8 * s, 96);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WT_WORKERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(WT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows past R (read only by the unused 4th lane group) must hold finite values
+  for (int i = tid; i < (xset - p.R * 128) / 16; i += WT_THREADS) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t o = (size_t)p.R * 128 + (size_t)i * 16;
+    *reinterpret_cast<float4*>(smem + p.off_x0 + o) = zero;
+    *reinterpret_cast<float4*>(smem + p.off_x0 + xset + o) = zero;
+    *reinterpret_cast<float4*>(smem + p.off_x1 + o) = zero;
+    *reinterpret_cast<float4*>(smem + p.off_x1 + xset + o) = zero;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -71,7 +85,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   if (warp < WT_WORKERS / 32) {
     // =============================== producers (+ warps 0-3: accumulator drain) =========================
     const int c4 = tid & 7, jrow = tid >> 3;
-    float macc[3][32];                      // fp32 master accumulators: taps warp, warp+4, warp+8
+    float macc[3][32];                      // fp32 master accumulators: taps (kh, kw = warp), lane = ci, [co]
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -160,67 +174,65 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         stage(u + 1);
       }
       const int it = u / p.npairs;
-      if (warp < 4 && (u - it * p.npairs) == p.npairs - 1) {
-        // ---- drain the tile's accumulators: lane = cout, 32 cin columns per tap --------------------------
-        mbar_wait(bar_tfull, it & 1);
+      if (warp < 3 && (u - it * p.npairs) == p.npairs - 1) {
+        // ---- drain the tile's accumulators: lane quarter = kw, lane = cin, 32 cout columns per kernel row ----
+        const int set = it & 1;
+        mbar_wait(bar_tfull + 8 * set, (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(set * 96);
         float v[32];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const int tap = warp + 4 * a;
-          if (tap < 9) {                         // warp-uniform
-            tmem_ld32(taddr + (uint32_t)(tap * 32), v);
+        for (int kh = 0; kh < 3; ++kh) {
+          tmem_ld32(taddr + (uint32_t)(kh * 32), v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) macc[a][c] += v[c];
-          }
+          for (int c = 0; c < 32; ++c) macc[kh][c] += v[c];
         }
         tc_fence_before();
-        mbar_arrive(bar_tfree);
+        mbar_arrive(bar_tfree + 8 * set);
       }
     }
-    if (warp < 4) {
+    if (warp < 3) {
       float* P = p.partial + ((long long)task * p.splits + split) * 9 * 32 * 32;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const int tap = warp + 4 * a;
-        if (tap < 9) {
+      for (int kh = 0; kh < 3; ++kh) {
+        float4* dst = reinterpret_cast<float4*>(P + ((kh * 3 + warp) * 32 + lane) * 32);
 #pragma unroll
-          for (int ci = 0; ci < 32; ++ci) P[(tap * 32 + ci) * 32 + lane] = macc[a][ci];
-        }
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_float4(macc[kh][4 * c], macc[kh][4 * c + 1], macc[kh][4 * c + 2], macc[kh][4 * c + 3]);
       }
     }
   } else {
     // ======================================= MMA issuer =================================================
     for (int u = 0; u < nunits; ++u) {
       const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
+      const int set = it & 1;
       mbar_wait(bar_full + 8 * s, (u >> 1) & 1);
-      if (pair == 0 && it >= 1) mbar_wait(bar_tfree, (it - 1) & 1);
+      if (pair == 0 && it >= 2) mbar_wait(bar_tfree + 8 * set, ((it - 2) >> 1) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
-        // descriptor low words (start address, LBO = 0); per MMA only the start field moves
-        const uint32_t x_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_x1 : p.off_x0)), 0u);
+        // descriptor low words (start address | LBO); per MMA only the start field moves.  A = x halo with
+        // LBO = one position row (lane group j = halo shifted by j rows), B = g tile.
+        const uint32_t x_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_x1 : p.off_x0)), 128u);
         const uint32_t x_lo0 = x_hi0 + (uint32_t)(xset >> 4);
         const uint32_t g_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_g1 : p.off_g0)), 0u);
         const uint32_t g_lo0 = g_hi0 + (uint32_t)(gset >> 4);
         constexpr uint32_t dhi = umma_desc_hi(512u, 1u);            // SBO 512 B, 128B-swizzle / 32B-base layout
-        uint32_t tapoff[9];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 8u;   // rows * 128 B / 16
+        const uint32_t d0 = tmem_base + (uint32_t)(set * 96);
+        const uint32_t rowoff = (uint32_t)p.Wp * 8u;                // one kernel row = Wp position rows (16 B units)
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t fresh = (pair == 0 && ks == 0) ? 0u : 1u;
           const uint32_t ko = (uint32_t)ks * 64u;                   // 8 position rows of 128 B per K step
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t bo = ko + tapoff[tap];
-            const uint32_t d = tmem_base + (uint32_t)(tap * 32);
-            umma_tf32_lh(d, g_lo0 + ko, dhi, x_hi0 + bo, dhi, WT_IDESC, fresh);
-            umma_tf32_lh(d, g_hi0 + ko, dhi, x_lo0 + bo, dhi, WT_IDESC, 1u);
-            umma_tf32_lh(d, g_hi0 + ko, dhi, x_hi0 + bo, dhi, WT_IDESC, 1u);
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t ao = ko + (uint32_t)kh * rowoff;
+            const uint32_t d = d0 + (uint32_t)(kh * 32);
+            umma_tf32_lh(d, x_lo0 + ao, dhi, g_hi0 + ko, dhi, WT_IDESC, fresh);
+            umma_tf32_lh(d, x_hi0 + ao, dhi, g_lo0 + ko, dhi, WT_IDESC, 1u);
+            umma_tf32_lh(d, x_hi0 + ao, dhi, g_hi0 + ko, dhi, WT_IDESC, 1u);
           }
         }
         umma_commit(bar_sfree + 8 * s);
-        if (pair == p.npairs - 1) umma_commit(bar_tfull);
+        if (pair == p.npairs - 1) umma_commit(bar_tfull + 8 * set);
       }
       __syncwarp();
     }
@@ -240,7 +252,8 @@ static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
   p.Q = g.n * p.Hp * p.Wp;
   p.tiles_per_task = (p.Q + 127) / 128;
   p.R = 128 + 2 * p.Wp + 2;
-  p.xbuf = ((p.R + 7) & ~7) * 128;                   // whole 1 KB units keep every buffer 1024 B aligned
+  p.xbuf = ((p.R + 1 + 7) & ~7) * 128;               // + the row the unused lane group reads; whole 1 KB units
+                                                     // keep every buffer 1024 B aligned
   const int gbuf = 128 * 128;
   p.off_x0 = 0;
   p.off_g0 = p.off_x0 + 2 * p.xbuf;

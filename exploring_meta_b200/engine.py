@@ -363,7 +363,8 @@ class MamlEngine(_EngineBase):
             b.mean_invstd, b.bwd_red, b.dual_red = _p(MI[l]), _p(BR[l]), _p(self.tDR[l])
             b.gamma, b.beta, b.gb_task_stride = _p(th, o[4 * l]), _p(th, o[4 * l + 1]), ts
             b.gamma_dot, b.beta_dot, b.gbdot_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
-            b.gz, b.gzdot = _p(self.GZ), _p(self.GZdot)
+            # gz is re-derived only where a consumer needs it: dgrad / wgrad pair 2 of layers with a tangent input
+            b.gz, b.gzdot = (_p(self.GZ) if l > 0 else None), _p(self.GZdot)
             b.out_gamma, b.out_beta, b.out_task_stride = _p(out, o[4 * l]), _p(out, o[4 * l + 1]), P
             b.base_gamma, b.base_beta, b.base_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
             b.scale = -self.lr

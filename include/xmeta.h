@@ -133,7 +133,7 @@ int xm_bn_bwd(const XmBnArgs* a, void* stream);
 /* reads z, zdot, dsums, mean_invstd, gamma(+dot), beta(+dot)   writes pdot, dual_red     */
 int xm_bn_dual_fwd(const XmBnArgs* a, void* stream);
 /* reads z, zdot, gp, gpdot, mean_invstd, bwd_red, dual_red, gamma(+dot), beta
- * writes gz (recomputed), gzdot, out_gamma/out_beta = base + scale * tangent of (g_gamma, g_beta) */
+ * writes gz (recomputed; NULL = not needed), gzdot, out_gamma/out_beta = base + scale * tangent of (g_gamma, g_beta) */
 int xm_bn_dual_bwd(const XmBnArgs* a, void* stream);
 
 /* xm_head: classifier head on block-4 features, one CTA per task, forward + loss + backward fused.
@@ -199,8 +199,9 @@ int xm_bn_ema(float* running_mean, float* running_var, const float* call_stats, 
  * accuracy, what the parity contract is stated in); 0 = single-pass TF32 (faster, ~1e-3 relative error
  * per contraction).  Process-wide; set before building / capturing a launch program. */
 int xm_set_precision(int precise);
-/* 1 (default): 32-channel stride-1 convolutions run on the tcgen05 / TMEM kernel; 0: every shape uses the
- * generic mma.sync kernel (A/B comparison and fallback). */
+/* Kernel selection for A/B comparison.  1 (default): 32-channel stride-1 contractions run on the tcgen05 / TMEM
+ * kernels and the image layer (cin <= 4, stride 1) on the exact-fp32 CUDA-core kernel; 2: the image-layer forward
+ * also runs on tcgen05; 0: every shape uses the generic mma.sync kernels. */
 int xm_set_tcgen05(int enable);
 
 int xm_version(void);

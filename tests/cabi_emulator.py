@@ -285,7 +285,8 @@ class EmulatedLib:
         proj = gbn - _bc(m1) - xhat * _bc(m2)
         gz = _bc(gamma * r) * proj
         gzd = _bc(gd * r + gamma * rdot) * proj + _bc(gamma * r) * (gbnd - _bc(e1) - xhd * _bc(m2) - xhat * _bc(e2 + q))
-        view(a.gz, gz.shape).copy_(gz)
+        if a.gz:
+            view(a.gz, gz.shape).copy_(gz)
         view(a.gzdot, gzd.shape).copy_(gzd)
         cnt = g.n * g.hz * g.wz
         axpy_out(a.out_gamma, a.out_task_stride, a.base_gamma, a.base_task_stride, a.scale, g.tasks, (e2 + q) * cnt)
