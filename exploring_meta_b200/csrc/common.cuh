@@ -76,6 +76,16 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, f
       : "+f"(d0), "+f"(d1) : "f"(a), "f"(b0), "f"(b1));
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zero (out-of-range halo elements).
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(CI_THREADS, 3) conv_img_kernel(const ConvImgK 
   const int cg = lane & 7, quad = lane >> 3;
   const int Wp = p.W + 2;
   float4* wsm = sm4;                                   // [9*CIN][8] float4: weights [tap][ci][co 32]
-  float4* band = sm4 + 9 * CIN * 8;                    // [CI_ROWS+2][Wp]
+  float4* band = sm4 + 9 * CIN * 8;                    // 2 x ([CI_ROWS+2][Wp] + 4 pad)
   __shared__ double sred[2][32];
 
   {
@@ -48,26 +48,41 @@ __global__ void __launch_bounds__(CI_THREADS, 3) conv_img_kernel(const ConvImgK 
       wf[i] = (co0 + co < p.cout) ? __ldg(Wt + ((long long)(co0 + co) * CIN + ci) * 9 + tap) : 0.f;
     }
     if (tid < 64) sred[tid >> 5][tid & 31] = 0.0;
-    if (tid < 4) band[(CI_ROWS + 2) * Wp + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   const int bands_per_img = (p.H + CI_ROWS - 1) / CI_ROWS;
   const int nbands = p.n * bands_per_img;
   const int chw = p.H * p.W;
 
-  for (int b = split; b < nbands; b += p.splits) {
+  // x bands are double-buffered: band k+1 streams in with cp.async (4 B per channel element, zero-filled
+  // outside the image) while band k is being convolved
+  const int band_px = (CI_ROWS + 2) * Wp + 4;
+  auto issue_band = [&](int b, float4* dst) {
     const int img = b / bands_per_img, y0 = (b - img * bands_per_img) * CI_ROWS;
     const float* X = p.x + ((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * CIN * chw;
-    __syncthreads();
     for (int i = tid; i < (CI_ROWS + 2) * Wp; i += CI_THREADS) {
       const int yy = i / Wp, xx = i - yy * Wp;
       const int y = y0 - 1 + yy, x = xx - 1;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+      const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
+      const float* src = in ? X + y * p.W + x : X;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) v[c] = __ldg(X + (long long)c * chw + y * p.W + x);
-      }
-      band[i] = make_float4(v[0], v[1], v[2], v[3]);
+      for (int c = 0; c < CIN; ++c)
+        cp_async4(reinterpret_cast<float*>(dst + i) + c, src + (in ? (long long)c * chw : 0), in ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+  for (int i = tid; i < 2 * band_px; i += CI_THREADS) band[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (split < nbands) issue_band(split, band);
+  int kbuf = 0;
+  for (int b = split; b < nbands; b += p.splits, kbuf ^= 1) {
+    const int img = b / bands_per_img, y0 = (b - img * bands_per_img) * CI_ROWS;
+    float4* const cur = band + kbuf * band_px;
+    if (b + p.splits < nbands) {
+      issue_band(b + p.splits, band + (kbuf ^ 1) * band_px);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     const int rows = min(CI_ROWS, p.H - y0);
@@ -100,7 +115,7 @@ __global__ void __launch_bounds__(CI_THREADS, 3) conv_img_kernel(const ConvImgK 
           float xv[4][4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float4 t = band[boff[u] + kh * Wp + kw];
+            const float4 t = cur[boff[u] + kh * Wp + kw];
             xv[u][0] = t.x; xv[u][1] = t.y; xv[u][2] = t.z; xv[u][3] = t.w;
           }
 #pragma unroll
@@ -131,6 +146,7 @@ __global__ void __launch_bounds__(CI_THREADS, 3) conv_img_kernel(const ConvImgK 
         }
       }
     }
+    __syncthreads();          // every warp is done with `cur` before the next iteration refills it
   }
   if (p.stat_mode) {
 #pragma unroll
@@ -161,7 +177,7 @@ int conv_img_try(const XmConvArgs* a, cudaStream_t stream) {
   k.out = a->out; k.aux = a->aux; k.stats = a->stats;
   const int cotiles = (g.cout + 31) / 32;
   const int nbands = g.n * ((g.hin + CI_ROWS - 1) / CI_ROWS);
-  const size_t smem = ((size_t)9 * g.cin * 8 + (size_t)(CI_ROWS + 2) * (g.win + 2) + 4) * 16;   // + 4 pad pixels
+  const size_t smem = ((size_t)9 * g.cin * 8 + 2 * ((size_t)(CI_ROWS + 2) * (g.win + 2) + 4)) * 16;   // 2 bands (+ 4 pad pixels)
   if (smem > 64 * 1024) return 0;
   const void* kern = g.cin == 1 ? (const void*)conv_img_kernel<1> : g.cin == 2 ? (const void*)conv_img_kernel<2>
                    : g.cin == 3 ? (const void*)conv_img_kernel<3> : (const void*)conv_img_kernel<4>;

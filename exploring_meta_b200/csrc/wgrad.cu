@@ -223,20 +223,36 @@ wgrad_img_kernel(const WgradImgK p) {
     for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
   const float* G = p.g + (long long)task * p.n * p.H * p.W * p.cout;
 
-  for (int band = split; band < nbands; band += p.splits) {
+  // x bands are double-buffered: band k+1 streams in with cp.async (zero-filled outside the image) while the
+  // g rows of band k are being reduced
+  const int band_px = (WI_ROWS + 2) * Wp + WI_UNROLL;
+  const int chw = p.H * p.W;
+  auto issue_band = [&](int band, float4* dst) {
     const int img = band / bands_per_img, y0 = (band - img * bands_per_img) * WI_ROWS;
-    const float* X = p.x + ((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * p.cin * p.H * p.W;
-    __syncthreads();
+    const float* X = p.x + ((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * p.cin * chw;
     for (int i = tid; i < (WI_ROWS + 2) * Wp; i += WI_THREADS) {
       const int yy = i / Wp, xx = i - yy * Wp;
       const int y = y0 - 1 + yy, x = xx - 1;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+      const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
+      const float* src = in ? X + y * p.W + x : X;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < p.cin) v[c] = __ldg(X + ((long long)c * p.H + y) * p.W + x);
-      }
-      sh4[i] = make_float4(v[0], v[1], v[2], v[3]);
+      for (int c = 0; c < 4; ++c)
+        if (c < p.cin) cp_async4(reinterpret_cast<float*>(dst + i) + c, src + (in ? (long long)c * chw : 0), in ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+  for (int i = tid; i < 2 * band_px; i += WI_THREADS) sh4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (split < nbands) issue_band(split, sh4);
+  int kbuf = 0;
+  for (int band = split; band < nbands; band += p.splits, kbuf ^= 1) {
+    const int img = band / bands_per_img, y0 = (band - img * bands_per_img) * WI_ROWS;
+    const float4* const cur = sh4 + kbuf * band_px;
+    if (band + p.splits < nbands) {
+      issue_band(band + p.splits, sh4 + (kbuf ^ 1) * band_px);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     const int rows = min(WI_ROWS, p.H - y0);
@@ -252,21 +268,22 @@ wgrad_img_kernel(const WgradImgK p) {
 #pragma unroll
       for (int u = 0; u < WI_UNROLL; ++u)
         gv[u] = (x0 + u < p.W && co < p.cout) ? __ldg(Gr + (long long)u * p.cout) : 0.f;
-      const float4* xrow = sh4 + ry * Wp + x0;
+      const float4* xrow = cur + ry * Wp + x0;
+      // (pixels past the row end carry gv = 0 and read the finite pad / next-row pixels: no predicate, so the
+      // unrolled loop shares the overlapping x loads of neighbouring pixels)
 #pragma unroll
       for (int u = 0; u < WI_UNROLL; ++u) {
-        if (x0 + u < p.W) {                           // warp-uniform
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const float4 xv = xrow[kh * Wp + u + kw];
-              ffma2(acc[kh * 3 + kw][0], acc[kh * 3 + kw][1], gv[u], xv.x, xv.y);
-              ffma2(acc[kh * 3 + kw][2], acc[kh * 3 + kw][3], gv[u], xv.z, xv.w);
-            }
-        }
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 xv = xrow[kh * Wp + u + kw];
+            ffma2(acc[kh * 3 + kw][0], acc[kh * 3 + kw][1], gv[u], xv.x, xv.y);
+            ffma2(acc[kh * 3 + kw][2], acc[kh * 3 + kw][3], gv[u], xv.z, xv.w);
+          }
       }
     }
+    __syncthreads();          // every warp is done with `cur` before the next iteration refills it
   }
   // cross-warp reduction, then one partial block per (task, split)
   __syncthreads();
@@ -289,7 +306,7 @@ wgrad_img_kernel(const WgradImgK p) {
 }
 
 static size_t wgrad_img_smem(const XmBlockGeom& g) {
-  size_t smem = (size_t)(WI_ROWS + 2) * (g.win + 2) * 16;
+  size_t smem = 2 * ((size_t)(WI_ROWS + 2) * (g.win + 2) + WI_UNROLL) * 16;     // two x bands (+ pad pixels)
   const size_t red = (size_t)8 * 36 * 32 * 4;
   return smem < red ? red : smem;
 }
