@@ -423,11 +423,12 @@ class AnilEngine(_EngineBase):
     in one kernel, then a first-order body backward.  Outputs: ``grad`` [P_body] and ``head_grad``
     [ways*D + ways] (sums over tasks, unscaled), ``loss``, ``correct``, ``call_stats`` [layers, tasks, 2, C]."""
 
-    def __init__(self, spec, tasks, shots, steps, inner_lr, first_order=False, device='cuda'):
+    def __init__(self, spec, tasks, shots, steps, inner_lr, first_order=False, device='cuda', mode='train'):
         super().__init__(spec, tasks, device)
-        assert spec.head == 'none'
+        assert spec.head == 'none' and mode in ('train', 'eval')
         self.shots, self.steps, self.lr = int(shots), int(steps), float(inner_lr)
         self.first_order = bool(first_order)
+        self.mode = mode              # 'eval': body forward + head adaptation + query metrics only (validation / test)
         self.S = spec.ways * self.shots
         self.rows = 2 * self.S
         B, L, C, P, R = self.tasks, spec.layers, self.C, self.P, self.rows
@@ -474,6 +475,8 @@ class AnilEngine(_EngineBase):
         self.head_scratch = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=self.device)
         h.scratch, h.scratch_bytes = _p(self.head_scratch), self.head_scratch.numel() * 4
         prog.emit('xm_anil_head', h)
+        if self.mode == 'eval':
+            return
         for l in reversed(range(L)):
             self._emit_block_bwd(prog, l, R, self.Pa[l - 1] if l else None, rows, self.theta, 0,
                                  self.Z[l], self.GP[l], self.MI[l], self.BR[l], self.GZ,

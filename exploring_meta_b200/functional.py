@@ -87,7 +87,8 @@ class _BlockForward(torch.autograd.Function):
         n, cin, hin, win = x.shape
         cout = weight.size(0)
         g = _geom(n, cin, cout, hin, win, stride, pool)
-        x, gamma, beta, weight = x.detach().float(), gamma.detach().contiguous(), beta.detach().contiguous(), \
+        x_in, gamma_in, beta_in, weight_in = x, gamma, beta, weight        # graph-connected: saved for backward
+        x, gamma, beta, weight = x.detach(), gamma.detach().contiguous(), beta.detach().contiguous(), \
             weight.detach().contiguous()
         z = torch.empty((n, g.hz, g.wz, cout), dtype=torch.float32, device=dev)
         p = torch.empty((n, g.hp, g.wp, cout), dtype=torch.float32, device=dev)
@@ -106,17 +107,15 @@ class _BlockForward(torch.autograd.Function):
         b.mean_invstd, b.call_stats, b.p, b.scratch = _ptr(mi), _ptr(stats), _ptr(p), _ptr(bn_scratch)
         _call('xm_bn_fwd', b, dev)
         ctx.geom = (n, cin, cout, hin, win, stride, pool)
-        ctx.save_for_backward(xs, gamma, beta, weight, z, mi)
-        ctx.x_is_image = bool(a.src_nchw)
+        ctx.save_for_backward(x_in, gamma_in, beta_in, weight_in, z, mi)
         ctx.mark_non_differentiable(stats)
         return _as_nchw(p), stats
 
     @staticmethod
     def backward(ctx, gp, _gstats):
-        xs, gamma, beta, weight, z, mi = ctx.saved_tensors
+        x, gamma, beta, weight, z, mi = ctx.saved_tensors
         need_x = ctx.needs_input_grad[0]
-        gx, ggamma, gbeta, gw = _BlockBackward.apply(xs, gamma, beta, weight, gp, z, mi, ctx.geom,
-                                                     ctx.x_is_image, need_x)
+        gx, ggamma, gbeta, gw = _BlockBackward.apply(x, gamma, beta, weight, gp, z, mi, ctx.geom, need_x)
         gbias = torch.zeros_like(gamma) if ctx.needs_input_grad[4] else None      # cancelled by train-mode BN
         return (gx if need_x else None), ggamma, gbeta, gw, gbias, None, None
 
@@ -125,11 +124,15 @@ class _BlockBackward(torch.autograd.Function):
     """(x, gamma, beta, W, g_p) -> (g_x, g_gamma, g_beta, g_W); z / mean_invstd are the forward's saved data."""
 
     @staticmethod
-    def forward(ctx, xs, gamma, beta, weight, gp, z, mi, geom, x_is_image, need_x):
+    def forward(ctx, x, gamma, beta, weight, gp, z, mi, geom, need_x):
         dev = z.device
         n, cin, cout, hin, win, stride, pool = geom
         g = _geom(*geom)
-        xs, gamma, beta, weight = xs.detach(), gamma.detach(), beta.detach(), weight.detach()
+        x_in, gamma_in, beta_in, weight_in, gp_in = x, gamma, beta, weight, gp
+        gamma, beta, weight = gamma.detach().contiguous(), beta.detach().contiguous(), weight.detach().contiguous()
+        probe = XmWgradArgs()
+        xs = _src(probe, x.detach())
+        x_is_image = bool(probe.src_nchw)
         gp = _nhwc(gp.detach().float())
         gz = torch.empty_like(z)
         bwd_red = torch.empty((2, cout), dtype=torch.float32, device=dev)
@@ -157,8 +160,8 @@ class _BlockBackward(torch.autograd.Function):
         w.x1, w.g1, w.out_w, w.scale = _ptr(xs), _ptr(gz), _ptr(gw), 1.0
         w.partial, w.partial_bytes = _ptr(wg_partial), wg_partial.numel() * 4
         _call('xm_wgrad', w, dev)
-        ctx.geom, ctx.x_is_image, ctx.need_x = geom, x_is_image, need_x
-        ctx.save_for_backward(xs, gamma, beta, weight, gp, z, mi, bwd_red)
+        ctx.geom, ctx.need_x = geom, need_x
+        ctx.save_for_backward(x_in, gamma_in, beta_in, weight_in, gp_in, z, mi, bwd_red)
         if gx is None:
             gx = torch.zeros((), device=dev)
             ctx.mark_non_differentiable(gx)
@@ -169,11 +172,18 @@ class _BlockBackward(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, ux, ugamma, ubeta, uw):
-        xs, gamma, beta, weight, gp, z, mi, bwd_red = ctx.saved_tensors
+        x, gamma, beta, weight, gp, z, mi, bwd_red = ctx.saved_tensors
         dev = z.device
         n, cin, cout, hin, win, stride, pool = ctx.geom
         g = _geom(*ctx.geom)
+        gamma, beta, weight = gamma.contiguous(), beta.contiguous(), weight.contiguous()
+        probe = XmWgradArgs()
+        xs = _src(probe, x)
+        x_is_image = bool(probe.src_nchw)
+        gp = _nhwc(gp.float())
         have_ux = ctx.need_x and ux is not None
+        if have_ux and x_is_image:            # src_nchw applies to both pairs of a call: a tangent input needs NHWC
+            xs, x_is_image = _nhwc(x), False
         ugamma = torch.zeros_like(gamma) if ugamma is None else ugamma.contiguous().float()
         ubeta = torch.zeros_like(beta) if ubeta is None else ubeta.contiguous().float()
         uw = torch.zeros_like(weight) if uw is None else uw.contiguous().float()
@@ -190,7 +200,7 @@ class _BlockBackward(torch.autograd.Function):
         # zdot = conv(x, Wdot) + conv(xdot, W)
         a = XmConvArgs()
         a.g, a.mode, a.stat_mode = g, XM_CONV_FWD, XM_STAT_SUM_AUX
-        if ctx.x_is_image:
+        if x_is_image:
             a.src_nchw, a.row0, a.row_step, a.rows_per_task = 1, 0, 1, n
         a.src1, a.w1 = _ptr(xs), _ptr(uw)
         if have_ux:
@@ -223,7 +233,7 @@ class _BlockBackward(torch.autograd.Function):
             gx_dot = _as_nchw(gx_dot)
         w = XmWgradArgs()
         w.g = g
-        if ctx.x_is_image:
+        if x_is_image:
             w.src_nchw, w.row0, w.row_step, w.rows_per_task = 1, 0, 1, n
         w.x1, w.g1 = _ptr(xs), _ptr(gzdot)
         if have_ux:
@@ -231,9 +241,9 @@ class _BlockBackward(torch.autograd.Function):
         w.out_w, w.scale = _ptr(gw_dot), 1.0
         w.partial, w.partial_bytes = _ptr(wg_partial), wg_partial.numel() * 4
         _call('xm_wgrad', w, dev)
-        if ctx.x_is_image and ctx.need_x:
+        if x_is_image and ctx.need_x:
             gx_dot = gx_dot.contiguous()
-        return gx_dot, ggamma_dot, gbeta_dot, gw_dot, _as_nchw(pdot), None, None, None, None, None
+        return gx_dot, ggamma_dot, gbeta_dot, gw_dot, _as_nchw(pdot), None, None, None, None
 
 
 def conv_block(x, gamma, beta, weight, bias=None, stride=1, pool=True):

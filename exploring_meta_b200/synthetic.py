@@ -45,3 +45,10 @@ class SyntheticTasks:
         x, y = make_tasks(tasks, self.ways, self.shots, self.in_shape, self._seed + self._count)
         self._count += tasks
         return x, y
+
+
+def get_tasks(dataset, ways, shots, seed=0):
+    """Stand-in for the reference's ``get_omniglot`` / ``get_mini_imagenet`` (``utils/data_pre.py:16-112``, learn2learn
+    datasets that need a download): three independent synthetic task streams ``(train, valid, test)``."""
+    shape = (1, 28, 28) if dataset == 'omni' else (3, 84, 84)
+    return tuple(SyntheticTasks(ways, shots, shape, seed=seed + 1_000_003 * k) for k in range(3))

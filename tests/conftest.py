@@ -23,3 +23,17 @@ def emulated_lib(monkeypatch):
     monkeypatch.setattr(_lib, '_lib', lib)
     monkeypatch.setattr(engine, '_require_cuda', lambda device: None)
     return lib
+
+
+@pytest.fixture(params=['emulator', pytest.param('cuda', marks=pytest.mark.gpu)])
+def kdev(request, monkeypatch):
+    """Device the reference-facing API tests run on: the CPU emulator of the C ABI (``-m "not gpu"``) or the real
+    library on cuda:0 (``-m gpu``)."""
+    import torch
+    if request.param == 'emulator':
+        import cabi_emulator
+        from exploring_meta_b200 import _lib, engine
+        monkeypatch.setattr(_lib, '_lib', cabi_emulator.EmulatedLib())
+        monkeypatch.setattr(engine, '_require_cuda', lambda device: None)
+        return torch.device('cpu')
+    return torch.device('cuda', 0)
