@@ -147,6 +147,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def family(name, cargs):
+    """Kernel family of one C-ABI call: the image layer (cin <= 4) runs on different kernels (CUDA-core FFMA2,
+    HBM-bound) than the 32-channel layers (tcgen05), so they are reported separately."""
+    if name in ('xm_conv', 'xm_wgrad') and cargs.g.cin <= 4:
+        return name + ':image_layer'
+    return name
+
+
 def kernel_breakdown(engine, reps=2):
     """Per-entry-point device time of one launch program, CUDA events on the launching stream around
     every C-ABI call (un-captured replay).  Returns {name: {'ms': per-step ms, 'calls': n}}."""
@@ -156,12 +164,13 @@ def kernel_breakdown(engine, reps=2):
     stream = torch.cuda.current_stream()
     calls = engine.prog.calls
     totals = {}
+    calls = [(fn, cargs, family(name, cargs)) for fn, cargs, name in calls]
     for rep in range(reps + 1):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in calls]
         for (fn, cargs, name), (e0, e1) in zip(calls, evs):
             e0.record(stream)
             code = fn(*cargs, stream.cuda_stream) if isinstance(cargs, tuple) else fn(ctypes.byref(cargs), stream.cuda_stream)
-            _lib.check(code, name)
+            _lib.check(code, name.split(':')[0])
             e1.record(stream)
         torch.cuda.synchronize()
         if rep == 0:
@@ -181,13 +190,20 @@ def program_work(engine):
     from exploring_meta_b200 import _lib
     work = {}
     for idx, (fn, a, name) in enumerate(engine.prog.calls):
-        w = work.setdefault(name, {'flops': 0.0, 'bytes': 0.0, 'per_call': {}})
+        fam = family(name, a)
+        w = work.setdefault(fam, {'flops': 0.0, 'bytes': 0.0, 'per_call': {}})
         if name in ('xm_conv', 'xm_wgrad'):
             g = a.g
             pairs = 2 if (getattr(a, 'src2', None) or getattr(a, 'x2', None)) else 1
             fl = 2.0 * g.tasks * g.n * g.hz * g.wz * 9 * g.cin * g.cout * pairs
             w['flops'] += fl
             w['per_call'][idx] = fl
+            if fam.endswith(':image_layer'):
+                # HBM-bound: the z-sized tensor (written by the conv / read by the wgrad) + the images
+                by = 4.0 * g.tasks * g.n * (g.hz * g.wz * g.cout + g.hin * g.win * g.cin)
+                if name == 'xm_conv' and a.stat_mode == 2:
+                    by += 4.0 * g.tasks * g.n * g.hz * g.wz * g.cout          # aux (z) read by the tangent pass
+                w['bytes'] += by
         elif name.startswith('xm_bn'):
             g = a.g
             z = 4.0 * g.tasks * g.n * g.hz * g.wz * g.cout
@@ -328,21 +344,38 @@ def run_ours(args):
                 fam['gbs'] = round(w['bytes'] / tv['ms'] / 1e6, 1)
             fams[name] = fam
         line['kernels'] = fams
+        def hbm_bound(name):
+            return name.startswith('xm_bn') or name.endswith(':image_layer')
+
+        for name, fam in fams.items():
+            if hbm_bound(name) and 'gbs' in fam:
+                fam['roofline_frac'] = round(fam['gbs'] / peaks['hbm_gbs'], 4)
+            elif 'tflops' in fam:
+                fam['roofline_frac'] = round(fam['tflops'] / peaks['tensor_tflops'], 4)
+        traffic = {}
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
         top = max(times.items(), key=lambda kv: kv[1]['ms'])[0]
         tv, w = times[top], work.get(top, {'flops': 0.0, 'bytes': 0.0})
-        if w['flops']:
-            achieved = w['flops'] / tv['ms'] / 1e9
-            line['roofline'] = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_tflops'],
-                                'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': None,
-                                'peak_source': peaks['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json); '
-                                'the kernel runs fp32-grade 3xTF32 on mma.sync, so its own ceiling is far lower',
-                                'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
-        else:
+        tr = traffic.get(top, {}).get('dram_bytes_per_launch')
+        if hbm_bound(top):
             achieved = w['bytes'] / tv['ms'] / 1e6
             line['roofline'] = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
-                                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
-                                'peak_source': peaks['source'], 'launches_per_step': tv['calls'],
-                                'avg_launch_ms': tv['ms'] / tv['calls']}
+                                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': tr,
+                                'peak_source': peaks['source'] + ' copy bandwidth (MEASURED_PEAKS.json)',
+                                'algorithmic_bytes_per_launch': w['bytes'] / tv['calls'],
+                                'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
+        else:
+            achieved = w['flops'] / tv['ms'] / 1e9
+            line['roofline'] = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_tflops'],
+                                'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': tr,
+                                'peak_source': peaks['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json); the '
+                                'kernel computes fp32-grade products as 3 TF32 tcgen05.mma each with N = 32 tiles, so '
+                                'its own ceiling is ~7% of this peak (DESIGN.md section 4)',
+                                'algorithmic_flops_per_launch': w['flops'] / tv['calls'],
+                                'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, times = cpu_reference_rate(2, 2, T)
         line['cpu_baseline'] = {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port',
