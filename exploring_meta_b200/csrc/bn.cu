@@ -59,12 +59,13 @@ struct Window {
   bool pooled;       // complete window with a pooled output (every element valid)
 };
 
-__device__ __forceinline__ Window make_window(const BnK& k, int task, long long item_px, int c0) {
-  // item_px indexes (img, wy, wx)
+__device__ __forceinline__ Window make_window(const BnK& k, int task, int item_px, int c0) {
+  // item_px indexes (img, wy, wx); 32-bit index arithmetic (the host checks n*wh*ww < 2^31)
   Window w;
-  const int wx = (int)(item_px % k.ww);
-  const int wy = (int)((item_px / k.ww) % k.wh);
-  const int img = (int)(item_px / ((long long)k.ww * k.wh));
+  const int row = item_px / k.ww;
+  const int wx = item_px - row * k.ww;
+  const int img = row / k.wh;
+  const int wy = row - img * k.wh;
   const long long zimg = ((long long)task * k.n + img) * k.hz;
   if (!k.pool) {
     w.zoff[0] = ((zimg + wy) * k.wz + wx) * k.C + c0;
@@ -168,10 +169,9 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const BnK k) {
     }
   }
   // pooled windows only: wh/ww are set to hp/wp by the host for this kernel
-  const long long items = (long long)k.n * k.wh * k.ww * cq;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float out[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) out[v] = 0.f;       // ReLU floor
@@ -201,10 +201,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnK k) {
   double acc[2][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[0][v] = acc[1][v] = 0.0;
-  const long long items = (long long)k.n * k.wh * k.ww * cq;     // host sets wh/ww = hp/wp here
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // host sets wh/ww = hp/wp here
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float z[4][VEC];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -256,10 +255,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnK k) {
       }
     }
   }
-  const long long items = (long long)k.n * k.wh * k.ww * cq;     // all windows, incl. odd edges
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // all windows, incl. odd edges
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float z[4][VEC];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -310,10 +308,9 @@ __global__ void __launch_bounds__(256) bn_dual_fwd_kernel(const BnK k) {
       k.dual_red[((long long)task * 2 + 1) * k.C + c0 + v] = d2[v];
     }
   }
-  const long long items = (long long)k.n * k.wh * k.ww * cq;     // pooled windows (host sets hp/wp)
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // pooled windows (host sets hp/wp)
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float z[4][VEC], zd[4][VEC];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -350,10 +347,9 @@ __global__ void __launch_bounds__(256) bn_dual_bwd_reduce_kernel(const BnK k) {
   double acc[3][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[0][v] = acc[1][v] = acc[2][v] = 0.0;
-  const long long items = (long long)k.n * k.wh * k.ww * cq;     // pooled windows
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // pooled windows
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float z[4][VEC], zd[4][VEC];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -414,10 +410,9 @@ __global__ void __launch_bounds__(256) bn_dual_bwd_apply_kernel(const BnK k) {
       k.out_beta[(long long)task * k.out_stride + c0 + v] = bb + k.scale * (float)(s1 * k.cnt);
     }
   }
-  const long long items = (long long)k.n * k.wh * k.ww * cq;     // all windows
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const Window w = make_window(k, task, it / cq, c0);
+  const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // all windows
+  for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
+    const Window w = make_window(k, task, px, c0);
     float z[4][VEC], zd[4][VEC];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -475,6 +470,7 @@ static int fill(const XmBnArgs* a, BnK& k, bool pooled_grid, int& vec, int& thre
   if (cq > 256) return 0;
   threads = (256 / cq) * cq;
   const long long items = (long long)g.n * k.wh * k.ww * cq;
+  if ((long long)g.n * k.wh * k.ww >= (1LL << 31)) return 0;
   long long want = (items + threads - 1) / threads;
   blocks = (int)(want < 65535 ? want : 65535);      // BN_LAUNCH clamps to one resident wave of the kernel
   if (blocks < 1) blocks = 1;

@@ -33,38 +33,40 @@
 
 namespace xm {
 
-constexpr int TC_PRODUCERS = 256;     // warps 0-7
-constexpr int TC_DRAINERS = 128;      // warps 8-11
-constexpr int TC_THREADS = TC_PRODUCERS + TC_DRAINERS + 32;   // + the MMA-issuing warp
-constexpr int TC_TMEM_COLS = 256;     // 2 stages x 4 accumulators x 32 columns
-constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 32, 0, 0);   // A and B K-major
+constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs  (12 warps = 3 per scheduler: 168 registers each)
+constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11 [, 12-15])
+constexpr int TC_GROUPS = 1;          // drain groups: group g drains tiles g, g + TC_GROUPS, ... (TMEM set = tile & 1)
+constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
+constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows minus the two shifted-out rows
+constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
+constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
 
 struct ConvTcK {
   int tasks, n, H, W, Hp, Wp;        // source == output spatial dims (stride 1)
+  PosMap pm;
   int Q;                             // positions per task = n*Hp*Wp
   int tiles_per_task;
   int R, plane_bytes;                // staged rows per tile, bytes per channel-group plane
   int wmode;                         // 0 forward, 1 data-gradient (transposed weights, flipped taps)
   int stat_mode, accumulate;
-  int cin, row0, row_step, rows_per_task;   // image layer: source = user images [task][row][c][H][W]
   const float* src; const float* w; long long wstride;
   float* out; const float* aux; double* stats;
 };
 
-template <bool IMG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int task = blockIdx.y;
-  constexpr int NPLANES = IMG ? 1 : 8;            // channel-group planes of the A operand
-  constexpr int BSLOTS = IMG ? 10 : 72;           // [slot][cout 32][4]: image layer 9 taps + a zero slot
+  constexpr int NPLANES = 8;                      // channel-group planes of the A operand
+  constexpr int BFLOATS = 3 * 8 * 96 * 4;         // B[kh][c4][n = kw*32 + cout][4]
   const int plane = p.plane_bytes, set_bytes = NPLANES * plane;   // one hi (or lo) set
 
   float* Bhi = reinterpret_cast<float*>(smem);
-  float* Blo = Bhi + BSLOTS * 32 * 4;
-  unsigned char* Abase = smem + 2 * BSLOTS * 32 * 4 * 4;       // stage s: hi at s*2*set, lo at (s*2+1)*set
+  float* Blo = Bhi + BFLOATS;
+  unsigned char* Abase = smem + 2 * BFLOATS * 4;               // stage s: hi at s*2*set, lo at (s*2+1)*set
   uint64_t* bars = reinterpret_cast<uint64_t*>(Abase + 4 * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(bars + 10);            // [4 buffers][4 warps][3][16] boundary rows
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
                  bar_tfree = smem_u32(bars + 6);
 
@@ -77,37 +79,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == 7) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // ---- resident weights, split into TF32 hi / lo ---------------------------------------------------------
+  // ---- resident weights, split into TF32 hi / lo: B[kh][k/4][n = kw*32 + out channel][k%4] ---------------
   {
     const float* W = p.w + (long long)task * p.wstride;       // [co][ci][3][3]
-    if (IMG) {
-      for (int i = tid; i < BSLOTS * 32 * 4; i += TC_THREADS) { Bhi[i] = 0.f; Blo[i] = 0.f; }
-      __syncthreads();
-      for (int i = tid; i < 32 * p.cin * 9; i += TC_THREADS) {
-        const int tap = i % 9, ci = (i / 9) % p.cin, co = i / (9 * p.cin);
-        const float v = __ldg(W + i);
-        const int idx = (tap * 32 + co) * 4 + ci;
-        const float hi = __uint_as_float(f2tf32(v));
-        Bhi[idx] = hi;
-        Blo[idx] = v - hi;
-      }
-    } else {
-      for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
-        const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[a][b][tap]
-        const float v = __ldg(W + i);
-        int n, k, t2;
-        if (p.wmode == 0) { n = a; k = b; t2 = tap; }           // forward: n = cout, k = cin
-        else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
-        const int idx = ((t2 * 8 + (k >> 2)) * 32 + n) * 4 + (k & 3);
-        const float hi = __uint_as_float(f2tf32(v));
-        Bhi[idx] = hi;
-        Blo[idx] = v - hi;
-      }
+    for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
+      const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[a][b][tap]
+      const float v = __ldg(W + i);
+      int n, k, t2;
+      if (p.wmode == 0) { n = a; k = b; t2 = tap; }           // forward: n = cout, k = cin
+      else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
+      const int kh = t2 / 3, kw = t2 - 3 * kh;
+      const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
+      const float hi = __uint_as_float(f2tf32(v));
+      Bhi[idx] = hi;
+      Blo[idx] = v - hi;
     }
   }
   fence_proxy_async();
@@ -119,134 +109,189 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   const int ntiles = (p.tiles_per_task - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // my tiles
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp < 8) {
+  if (warp < 7) {
     // ========================================= producers =============================================
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it & 1;
-      if (it >= 2) mbar_wait(bar_sfree + 8 * s, ((it - 2) >> 1) & 1);   // MMAs of tile it-2 have read stage s
-      const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
-      if (IMG) {
-        // one plane: row j <-> position q0 - Wp - 1 + j, 4 floats = (c0, c1, c2, 0) gathered from NCHW planes
-        unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes;
-        unsigned char* lo = hi + set_bytes;
-        for (int j = tid; j < p.R; j += TC_PRODUCERS) {
-          const int q = q0 - p.Wp - 1 + j;
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (q >= 0 && q < p.Q) {
-            const int img = q / HpWp, rem = q - img * HpWp;
-            const int r = rem / p.Wp, c = rem - r * p.Wp;
-            if (r >= 1 && c < p.W) {
-              const float* X = p.src + (((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * p.cin)
-                                       * p.H * p.W + (long long)(r - 1) * p.W + c;
+    // staged row j of a tile <-> position q0 - 1 - Wp + j  (q0 = first output position of the tile)
+    // Register-level software pipeline: the global loads of tile it+1 are issued BEFORE tile it is converted
+    // and stored, so the HBM/L2 latency overlaps the shared-memory phase and the wait for the stage.
+    constexpr int PR = TC_PRODUCERS / 4;                       // rows staged per pass: a thread moves 8 channels
+    const int c8 = tid & 3, jrow = tid >> 2;                   // channel octet (two planes), first row (0..PR-1)
+    const float* S = p.src + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
+    auto issue_loads = [&](int it, float4 (&v)[8]) {
+      const int qbase = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE - p.Wp - 1 + jrow;
 #pragma unroll
-              for (int ch = 0; ch < 4; ++ch)
-                if (ch < p.cin) v[ch] = __ldg(X + (long long)ch * p.H * p.W);
-            }
-          }
+      for (int u = 0; u < 4; ++u) {                              // 4 independent rows: no carried state
+        const int j = jrow + PR * u;
+        const int px = j < p.R ? pos_to_pixel(p.pm, qbase + PR * u) : -1;
+        v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px >= 0) ldg256(S + (long long)px * 32, v[2 * u], v[2 * u + 1]);
+      }
+    };
+#ifdef XM_TC_TIMING
+    long long t_wait = 0, t_load = 0, t0;
+#endif
+    auto store_tile = [&](int it, const float4 (&v)[8]) {
+      const int s = it & 1;
+#ifdef XM_TC_TIMING
+      t0 = clock64();
+#endif
+      if (it >= 2) mbar_wait(bar_sfree + 8 * s, ((it - 2) >> 1) & 1);   // MMAs of tile it-2 have read stage s
+#ifdef XM_TC_TIMING
+      t_wait += clock64() - t0; t0 = clock64();
+#endif
+      unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)(2 * c8) * plane;
+      unsigned char* lo = hi + set_bytes;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jrow + PR * u;
+        if (j < p.R) {
           float4 h, l;
-          h.x = __uint_as_float(f2tf32(v[0])); l.x = v[0] - h.x;
-          h.y = __uint_as_float(f2tf32(v[1])); l.y = v[1] - h.y;
-          h.z = __uint_as_float(f2tf32(v[2])); l.z = v[2] - h.z;
-          h.w = __uint_as_float(f2tf32(v[3])); l.w = v[3] - h.w;
+          split_tf32_fast(v[2 * u], h, l);
           *reinterpret_cast<float4*>(hi + (size_t)j * 16) = h;
           *reinterpret_cast<float4*>(lo + (size_t)j * 16) = l;
-        }
-      } else {
-        const int c4 = tid & 7, jrow = tid >> 3;                 // channel group, first row (0..31)
-        const float* S = p.src + (long long)task * p.n * p.H * p.W * 32;
-        unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)c4 * plane;
-        unsigned char* lo = hi + set_bytes;
-        // position of this thread's first row, then advanced incrementally by 32 positions per row step
-        int q = q0 - p.Wp - 1 + jrow;
-        int img, r, c;
-        if (q >= 0) { img = q / HpWp; const int rem = q - img * HpWp; r = rem / p.Wp; c = rem - r * p.Wp; }
-        else { img = -1; r = p.Hp - 1; c = q + p.Wp; if (c < 0) { c += p.Wp; r -= 1; } }   // q >= -Wp-1
-        for (int j0 = jrow; j0 < p.R; j0 += 256) {
-          float4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + 32 * u;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < p.R && img >= 0 && img < p.n && r >= 1 && c < p.W)
-              v[u] = __ldg(reinterpret_cast<const float4*>(S + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
-            c += 32;
-            while (c >= p.Wp) { c -= p.Wp; r += 1; }
-            while (r >= p.Hp) { r -= p.Hp; img += 1; }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + 32 * u;
-            if (j < p.R) {
-              float4 h, l;
-              h.x = __uint_as_float(f2tf32(v[u].x)); l.x = v[u].x - h.x;
-              h.y = __uint_as_float(f2tf32(v[u].y)); l.y = v[u].y - h.y;
-              h.z = __uint_as_float(f2tf32(v[u].z)); l.z = v[u].z - h.z;
-              h.w = __uint_as_float(f2tf32(v[u].w)); l.w = v[u].w - h.w;
-              *reinterpret_cast<float4*>(hi + (size_t)j * 16) = h;
-              *reinterpret_cast<float4*>(lo + (size_t)j * 16) = l;
-            }
-          }
+          split_tf32_fast(v[2 * u + 1], h, l);
+          *reinterpret_cast<float4*>(hi + plane + (size_t)j * 16) = h;
+          *reinterpret_cast<float4*>(lo + plane + (size_t)j * 16) = l;
         }
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+#ifdef XM_TC_TIMING
+      t_load += clock64() - t0;
+#endif
+    };
+    // two register buffers used alternately (loop unrolled by two: no register moves that would wait on loads)
+    float4 va[8], vb[8];
+    if (ntiles > 0) issue_loads(0, va);
+#ifdef XM_TC_TIMING
+    long long t_iss = 0, t1;
+#define XM_T_ISS(stmt) do { t1 = clock64(); stmt; t_iss += clock64() - t1; } while (0)
+#else
+#define XM_T_ISS(stmt) do { stmt; } while (0)
+#endif
+    for (int it = 0; it < ntiles; it += 2) {
+      if (it + 1 < ntiles) XM_T_ISS(issue_loads(it + 1, vb));
+      store_tile(it, va);
+      if (it + 1 < ntiles) {
+        if (it + 2 < ntiles) XM_T_ISS(issue_loads(it + 2, va));
+        store_tile(it + 1, vb);
+      }
     }
-  } else if (warp < 12) {
+#ifdef XM_TC_TIMING
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+      printf("producer: tiles %d wait %lld store %lld issue-loads %lld (per tile %lld / %lld / %lld)\n", ntiles, t_wait,
+             t_load, t_iss, t_wait / ntiles, t_load / ntiles, t_iss / ntiles);
+#endif
+  } else if (warp >= 8) {
     // ========================================== drainers =============================================
-    const int quarter = warp & 3;                              // TMEM lane quarter of this warp
+    // Accumulator row i (TMEM lane) holds, for position q0 - 1 + i, the three kw partial sums
+    // D[i][kw*32 + c]; output position q0 + i = D[i][kw=0] + D[i+1][kw=1] + D[i+2][kw=2]: the kw = 1 / 2 blocks
+    // come from the next two lanes (shuffles; the last two lanes of a warp take them from the next warp through
+    // a small shared-memory exchange).  Rows 126 and 127 of a tile produce no output.
+    const int quarter = warp & 3;                              // TMEM lane quarter of this warp (= warp id % 4)
+    const int group = (warp - 8) >> 2;
+    const int row = quarter * 32 + lane;
     float ssum[32], ssq[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.f;
-    for (int it = 0; it < ntiles; ++it) {
+#ifdef XM_TC_TIMING
+    long long t_wait = 0, t_tmem = 0, t_rest = 0, t0;
+#endif
+    for (int it = group; it < ntiles; it += TC_GROUPS) {
       const int s = it & 1;
+#ifdef XM_TC_TIMING
+      t0 = clock64();
+#endif
       mbar_wait(bar_tfull + 8 * s, (it >> 1) & 1);
+#ifdef XM_TC_TIMING
+      t_wait += clock64() - t0; t0 = clock64();
+#endif
       tc_fence_after();
-      // row (32*quarter + lane) of the tile
-      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + quarter * 32 + lane;
-      bool valid = false;
-      long long o = 0;
-      if (q < p.Q) {
-        const int img = q / HpWp, rem = q - img * HpWp;
-        const int r = rem / p.Wp, c = rem - r * p.Wp;
-        valid = r >= 1 && c < p.W;
-        o = ((((long long)task * p.n + img) * p.H + (r - 1)) * p.W + c) * 32;
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128);
+      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE + row;
+      const int px = row < TC_TILE ? pos_to_pixel(p.pm, q) : -1;
+      const bool valid = px >= 0;
+      const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * 32;
+      const long long o_pair = __shfl_xor_sync(0xffffffffu, o, 1);
+      const bool v_pair = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 192);
+      // ---- TMEM phase: both 16-column halves -> registers (kw shifts applied), then the set is released --------
+      auto load_half = [&](int half, float (&acc)[16]) {
+        // one 16-column block at a time (register pressure): kw = 1, kw = 2, then the thread's own kw = 0 block
+        float* xb = xch + ((((it & 1) * 2 + half) * 4 + quarter) * 3) * 16;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[16];
-        uint32_t rr[16];
-        tmem_ld16_nowait(taddr + 96 + half * 16, rr);            // correction terms first (small)
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(rr[k]);
-#pragma unroll
-        for (int a = 0; a < (IMG ? 1 : 3); ++a) {                // hi*hi terms of kernel rows 0..2
-          tmem_ld16_nowait(taddr + 32 * a + half * 16, rr);
+        for (int blk = 1; blk <= 3; ++blk) {
+          const int kw = blk % 3;                                  // 1, 2, 0
+          uint32_t r1[16], r2[16];
+          float v[16];
+          tmem_ld16_nowait(taddr + 96 + kw * 32 + half * 16, r1);  // correction terms (small)
+          tmem_ld16_nowait(taddr + kw * 32 + half * 16, r2);       // hi*hi terms
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] += __uint_as_float(rr[k]);
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
+          if (kw == 1) {
+            // boundary rows for the previous warp: lane 0 publishes its kw = 1 block
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) xb[k] = v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float t = __shfl_down_sync(0xffffffffu, v[k], 1);
+              acc[k] = lane < 31 ? t : 0.f;
+            }
+          } else if (kw == 2) {
+            if (lane < 2) {                                         // lanes 0 and 1 publish their kw = 2 blocks
+#pragma unroll
+              for (int k = 0; k < 16; ++k) xb[16 + lane * 16 + k] = v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float t = __shfl_down_sync(0xffffffffu, v[k], 2);
+              acc[k] += lane < 30 ? t : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] += v[k];
+          }
         }
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(bar_tfree + 8 * s);                        // TMEM set s may be overwritten
+      };
+      float acc2[2][16];
+      load_half(0, acc2[0]);
+      load_half(1, acc2[1]);
+      tc_fence_before();
+      mbar_arrive(bar_tfree + 8 * s);                            // TMEM set s may be overwritten
+#ifdef XM_TC_TIMING
+      t_tmem += clock64() - t0; t0 = clock64();
+#endif
+      if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the group's four warps: boundary rows published
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (lane >= 30) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
+          const float* xn = xch + ((((it & 1) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc2[half][k] += lane == 31 ? xn[k] + xn[32 + k] : xn[16 + k];
         }
+      }
+      // ---- epilogue of both halves: (accumulate), statistics, paired full-sector stores --------------------------
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float (&acc)[16] = acc2[half];
         if (valid) {
-          float4* dst = reinterpret_cast<float4*>(p.out + o + half * 16);
           if (p.accumulate) {
+            const float4* old4 = reinterpret_cast<const float4*>(p.out + o + half * 16);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float4 old = dst[k];
-              v[4 * k] += old.x; v[4 * k + 1] += old.y; v[4 * k + 2] += old.z; v[4 * k + 3] += old.w;
+              const float4 old = old4[k];
+              acc[4 * k] += old.x; acc[4 * k + 1] += old.y; acc[4 * k + 2] += old.z; acc[4 * k + 3] += old.w;
             }
           }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           if (p.stat_mode == XM_STAT_SUM_SQ) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              ssum[half * 16 + k] += v[k];
-              ssq[half * 16 + k] = fmaf(v[k], v[k], ssq[half * 16 + k]);
+              ssum[half * 16 + k] += acc[k];
+              ssq[half * 16 + k] = fmaf(acc[k], acc[k], ssq[half * 16 + k]);
             }
           } else if (p.stat_mode == XM_STAT_SUM_AUX) {
             const float4* ax = reinterpret_cast<const float4*>(p.aux + o + half * 16);
@@ -254,14 +299,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
             for (int k = 0; k < 4; ++k) {
               const float4 a4 = __ldg(ax + k);
               const int b = half * 16 + 4 * k;
-              ssum[b] += v[4 * k]; ssum[b + 1] += v[4 * k + 1]; ssum[b + 2] += v[4 * k + 2]; ssum[b + 3] += v[4 * k + 3];
-              ssq[b] = fmaf(v[4 * k], a4.x, ssq[b]); ssq[b + 1] = fmaf(v[4 * k + 1], a4.y, ssq[b + 1]);
-              ssq[b + 2] = fmaf(v[4 * k + 2], a4.z, ssq[b + 2]); ssq[b + 3] = fmaf(v[4 * k + 3], a4.w, ssq[b + 3]);
+              ssum[b] += acc[4 * k]; ssum[b + 1] += acc[4 * k + 1]; ssum[b + 2] += acc[4 * k + 2]; ssum[b + 3] += acc[4 * k + 3];
+              ssq[b] = fmaf(acc[4 * k], a4.x, ssq[b]); ssq[b + 1] = fmaf(acc[4 * k + 1], a4.y, ssq[b + 1]);
+              ssq[b + 2] = fmaf(acc[4 * k + 2], a4.z, ssq[b + 2]); ssq[b + 3] = fmaf(acc[4 * k + 3], a4.w, ssq[b + 3]);
             }
+          }
+        }
+        // Store with full 32-byte sectors: lanes (2i, 2i+1) swap half of their float4s so that in every store
+        // instruction the pair writes 32 contiguous bytes of ONE row (a thread's own row is 4 float4 = 64 B of
+        // this half; 16-byte pieces of 32 different rows per instruction would be partial-sector writes).
+        {
+          const bool odd = lane & 1;
+          float rx[4], ry[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rx[k] = __shfl_xor_sync(0xffffffffu, odd ? acc[k] : acc[4 + k], 1);        // odd sends #0, even sends #1
+            ry[k] = __shfl_xor_sync(0xffffffffu, odd ? acc[8 + k] : acc[12 + k], 1);   // odd sends #2, even sends #3
+          }
+          // even lane: own #0, own #2, partner's #0, partner's #2;  odd lane: partner's #1, partner's #3, own #1, own #3
+          const long long o_first = odd ? o_pair : o, o_second = odd ? o : o_pair;
+          const bool v_first = odd ? v_pair : valid, v_second = odd ? valid : v_pair;
+          const int col = half * 16 + (odd ? 4 : 0);
+#ifdef XM_TC_NOSTORE
+          if (acc[0] != 123456.f) continue;
+#endif
+          if (v_first) {
+            float4* d = reinterpret_cast<float4*>(p.out + o_first + col);
+            d[0] = odd ? make_float4(rx[0], rx[1], rx[2], rx[3]) : make_float4(acc[0], acc[1], acc[2], acc[3]);
+            d[2] = odd ? make_float4(ry[0], ry[1], ry[2], ry[3]) : make_float4(acc[8], acc[9], acc[10], acc[11]);
+          }
+          if (v_second) {
+            float4* d = reinterpret_cast<float4*>(p.out + o_second + col);
+            d[0] = odd ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(rx[0], rx[1], rx[2], rx[3]);
+            d[2] = odd ? make_float4(acc[12], acc[13], acc[14], acc[15]) : make_float4(ry[0], ry[1], ry[2], ry[3]);
           }
         }
       }
     }
+#ifdef XM_TC_TIMING
+    t_rest = clock64() - t0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == TC_PRODUCERS + 32)
+      printf("drainer: wait %lld tmem-phase %lld (per tile %lld / %lld) last-rest %lld\n", t_wait, t_tmem,
+             t_wait / ntiles, t_tmem / ntiles, t_rest);
+#endif
     if (p.stat_mode) {
       // per-thread fp32 partials (<= a few hundred terms each) -> double across the warp -> global atomics
 #pragma unroll
@@ -276,92 +356,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     }
   } else {
     // ======================================= MMA issuer =================================================
+    // per tile: for every kernel row kh and channel octet ks, ONE A tile (the halo at row offset kh*Wp) against
+    // the [8 x 96] weight slab of the three kw taps; 3 expansion terms -> 36 MMAs (M=128, N=96, K=8).
+#ifdef XM_TC_TIMING
+    long long t_wf = 0, t_wt = 0, t_issue = 0, t0;
+#endif
     for (int it = 0; it < ntiles; ++it) {
       const int s = it & 1;
+#ifdef XM_TC_TIMING
+      t0 = clock64();
+#endif
       mbar_wait(bar_full + 8 * s, (it >> 1) & 1);
+#ifdef XM_TC_TIMING
+      t_wf += clock64() - t0; t0 = clock64();
+#endif
       if (it >= 2) mbar_wait(bar_tfree + 8 * s, ((it - 2) >> 1) & 1);
+#ifdef XM_TC_TIMING
+      t_wt += clock64() - t0; t0 = clock64();
+#endif
       tc_fence_after();
       if (elect_one_sync()) {
         // descriptor low words (start address | LBO) of the stage; per MMA only the start field moves
         const uint32_t a_base = smem_u32(Abase + (size_t)(2 * s) * set_bytes);
-        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 512u), b_lo0 = umma_desc_lo(smem_u32(Blo), 512u);
+        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 96u * 16u), b_lo0 = umma_desc_lo(smem_u32(Blo), 96u * 16u);
         constexpr uint32_t dhi = umma_desc_hi(128u);
-        const uint32_t d0 = tmem_base + (uint32_t)(s * 128);
-        if (IMG) {
-          // K = 8 = two taps x (3 channels + zero); tap pairs (0,1) (2,3) (4,5) (6,7) (8, zero slot)
+        const uint32_t d0 = tmem_base + (uint32_t)(s * 192);
+        const uint32_t a_hi0 = umma_desc_lo(a_base, (uint32_t)plane);
+        const uint32_t a_lo0 = a_hi0 + (uint32_t)(set_bytes >> 4);
+        const uint32_t kstep = (uint32_t)(2 * plane) >> 4;          // two channel-group planes per K = 8
 #pragma unroll
-          for (int pr = 0; pr < 5; ++pr) {
-            const int t0 = 2 * pr, t1 = 2 * pr + 1;
-            const uint32_t off0 = (uint32_t)((t0 / 3) * p.Wp + (t0 % 3));
-            const uint32_t off1 = pr < 4 ? (uint32_t)((t1 / 3) * p.Wp + (t1 % 3)) : off0;   // zero slot: LBO = 0
-            const uint32_t a_hi = umma_desc_lo(a_base + off0 * 16u, (off1 - off0) * 16u);
-            const uint32_t a_lo = a_hi + (uint32_t)(set_bytes >> 4);
-            const uint32_t bo = (uint32_t)(t0 * 32);                       // 16 B units: slot t0, next slot at LBO
-            umma_tf32_lh(d0 + 96, a_lo, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)(pr != 0));
-            umma_tf32_lh(d0 + 96, a_hi, dhi, b_lo0 + bo, dhi, TC_IDESC, 1u);
-            umma_tf32_lh(d0, a_hi, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)(pr != 0));
-          }
-        } else {
-          const uint32_t a_hi0 = umma_desc_lo(a_base, (uint32_t)plane);
-          const uint32_t a_lo0 = a_hi0 + (uint32_t)(set_bytes >> 4);
-          const uint32_t kstep = (uint32_t)(2 * plane) >> 4;          // two channel-group planes per K = 8
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t shift = (uint32_t)(kh * p.Wp);             // 16 B units (one staged row = 16 B per plane)
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t shift = (uint32_t)(kh * p.Wp + kw);      // 16 B units
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t ao = shift + (uint32_t)ks * kstep;
-                const uint32_t bo = (uint32_t)(((kh * 3 + kw) * 8 + 2 * ks) * 32);   // 16 B units, compile-time
-                umma_tf32_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | kw | ks) != 0));
-                umma_tf32_lh(d0 + 96, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC, 1u);
-                umma_tf32_lh(d0 + 32 * kh, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kw | ks) != 0));
-              }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ao = shift + (uint32_t)ks * kstep;
+            const uint32_t bo = (uint32_t)((kh * 8 + 2 * ks) * 96);   // 16 B units, compile-time
+#ifdef XM_TC_NOMMA
+            if (kh == 0 && ks == 0) {
+#endif
+            umma_tf32_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | ks) != 0));
+            umma_tf32_lh(d0 + 96, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC, 1u);
+            umma_tf32_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | ks) != 0));
+#ifdef XM_TC_NOMMA
             }
+#endif
           }
         }
         umma_commit(bar_sfree + 8 * s);     // shared-memory stage s consumed
         umma_commit(bar_tfull + 8 * s);     // accumulators of this tile complete
       }
       __syncwarp();
+#ifdef XM_TC_TIMING
+      t_issue += clock64() - t0;
+#endif
     }
+#ifdef XM_TC_TIMING
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+      printf("mma: wait-full %lld wait-tfree %lld issue %lld (per tile %lld / %lld / %lld)\n", t_wf, t_wt, t_issue,
+             t_wf / ntiles, t_wt / ntiles, t_issue / ntiles);
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 7) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
-static size_t conv_tc_smem(bool img, int Wp, int& R, int& plane_bytes) {
-  R = 128 + 2 * Wp + 2;
+static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
+  R = 128 + 2 * Wp;
   const int rpad = R | 1;                 // odd row count per plane: conflict-free 16 B stores across planes
   plane_bytes = rpad * 16;
-  const int nplanes = img ? 1 : 8, bslots = img ? 10 : 72;
-  return (size_t)2 * bslots * 32 * 4 * 4 + (size_t)4 * nplanes * plane_bytes + 8 * 8 + 16;
+  return (size_t)2 * (3 * 8 * 96 * 4) * 4 + (size_t)4 * 8 * plane_bytes + 10 * 8 + 4 * 4 * 3 * 16 * 4;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
 // <0 / >0 on error like every entry point.
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
-  const bool img = a->src_nchw != 0;
-  if (g.cout != 32 || g.stride != 1) return 0;
-  if (img) { if (g.cin > 4 || a->mode != XM_CONV_FWD || a->src2) return 0; }
-  else if (g.cin != 32) return 0;
+  if (g.cout != 32 || g.cin != 32 || g.stride != 1 || a->src_nchw) return 0;
   int R, plane_bytes;
-  const size_t smem = conv_tc_smem(img, g.win + 1, R, plane_bytes);
-  if (smem > 227 * 1024) return 0;
+  const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes);
+  if (smem > 227 * 1024 || R > TC_PRODUCERS) return 0;      // each producer thread stages <= 4 rows per tile
   ConvTcK p{};
   p.tasks = g.tasks; p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
   p.Q = g.n * p.Hp * p.Wp;
-  p.tiles_per_task = (p.Q + 127) / 128;
+  p.pm = make_posmap(g.n, g.hin, g.win);
+  p.tiles_per_task = (p.Q + TC_TILE - 1) / TC_TILE;
   p.R = R; p.plane_bytes = plane_bytes;
   p.wmode = a->mode == XM_CONV_FWD ? 0 : 1;
-  p.cin = g.cin; p.row0 = a->row0; p.row_step = a->row_step; p.rows_per_task = a->rows_per_task;
   p.out = a->out; p.aux = a->aux; p.stats = a->stats;
   int per_task = num_sms() / g.tasks;
   if (per_task < 1) per_task = 1;
@@ -369,8 +454,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   dim3 grid(per_task, g.tasks);
   static bool attr_set = false;
   if (!attr_set) {
-    XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * 32 * sizeof(double), stream));
@@ -381,8 +465,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
     p.accumulate = pair;                                   // second pair adds onto the first pass' output
     p.stat_mode = (pair == npairs - 1) ? a->stat_mode : 0; // statistics of the final values only
-    if (img) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
-    else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
     if (int rc = launched("xm_conv(tcgen05)")) return rc;
   }
   return 1;

@@ -119,4 +119,58 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// ---- flattened padded-pixel position arithmetic ----------------------------------------------------------------
+// Exact unsigned division by a run-time constant d >= 2 for numerators < 2^31: q / d == umulhi(q, mul) >> sh
+// (round-up magic number; verified exhaustively on the host side of the tests' shapes).  The producers map
+// hundreds of staged rows per tile from a position to an address; two 2-instruction divisions per row keep every
+// row's computation independent (instruction-level parallelism) instead of a serial carry chain.
+struct FastDiv { uint32_t mul, sh; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;                      // ceil(log2(d)), d >= 2
+  FastDiv f;
+  f.mul = (uint32_t)(((1ull << (31 + s)) / d) + 1ull);
+  f.sh = s - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t q, FastDiv d) { return __umulhi(q, d.mul) >> d.sh; }
+
+// Position sequence of one task: q = (img, r, c) with r in [0, H], c in [0, W]; row 0 and column W are padding.
+struct PosMap {
+  int n, H, W, Wp, HpWp;
+  FastDiv dimg, drow;
+};
+inline PosMap make_posmap(int n, int H, int W) {
+  PosMap m;
+  m.n = n; m.H = H; m.W = W; m.Wp = W + 1; m.HpWp = (H + 1) * (W + 1);
+  m.dimg = make_fastdiv((uint32_t)m.HpWp);
+  m.drow = make_fastdiv((uint32_t)m.Wp);
+  return m;
+}
+// Pixel index (img*H + y)*W + x of position q inside the task's [n][H][W] tensor, or -1 for padding / out of range.
+__device__ __forceinline__ int pos_to_pixel(const PosMap& m, int q) {
+  const uint32_t qq = (uint32_t)max(q, 0);
+  const int img = (int)fastdiv(qq, m.dimg);
+  const int rem = (int)qq - img * m.HpWp;
+  const int r = (int)fastdiv((uint32_t)rem, m.drow);
+  const int c = rem - r * m.Wp;
+  const bool ok = q >= 0 && img < m.n && r >= 1 && c < m.W;
+  return ok ? (img * m.H + r - 1) * m.W + c : -1;
+}
+
+// 256-bit read-only global load (sm_100: LDG.E.256): halves the number of load requests of the staging loops.
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+// x ~= hi + lo with hi = x rounded to TF32 (nearest, ties away -- the same value cvt.rna.tf32.f32 produces, computed
+// with two full-rate integer ops instead of the conversion pipe) and lo = x - hi (exact in fp32).
+__device__ __forceinline__ void split_tf32_fast(const float4& v, float4& h, float4& l) {
+  h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
+  h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); l.y = v.y - h.y;
+  h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); l.z = v.z - h.z;
+  h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); l.w = v.w - h.w;
+}
+
 }  // namespace xm

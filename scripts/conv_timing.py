@@ -1,0 +1,17 @@
+"""Role-level cycle breakdown of conv_tc_kernel (build with XM_NVCC_EXTRA=-DXM_TC_TIMING): one 42x42 forward launch."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from exploring_meta_b200 import _lib
+from exploring_meta_b200._lib import XmBlockGeom, XmConvArgs
+lib = _lib.load()
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 42
+g = XmBlockGeom(32, 25, 32, 32, H, H, H, H, H // 2, H // 2, 1, 1)
+x = torch.randn(32, 25, H, H, 32, device='cuda'); w = torch.randn(32, 32 * 32 * 9, device='cuda') * 0.05
+out = torch.empty_like(x); stats = torch.zeros(32, 2, 32, dtype=torch.float64, device='cuda')
+a = XmConvArgs(); a.g = g; a.mode = 0; a.stat_mode = 1
+a.src1, a.w1, a.w1_task_stride, a.out, a.stats = x.data_ptr(), w.data_ptr(), 9216, out.data_ptr(), stats.data_ptr()
+for _ in range(2):
+    _lib.check(lib.xm_conv(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), 'conv')
+    torch.cuda.synchronize()
+    print('---')

@@ -24,7 +24,8 @@ times = bench.kernel_breakdown(e, reps=3)
 work = bench.program_work(e)
 groups = collections.OrderedDict()
 for idx, (fn, args, name) in enumerate(e.prog.calls):
-    ms = times[name]['per_call'][idx]
+    fam = bench.family(name, args)
+    ms = times[fam]['per_call'][idx]
     key = name
     if hasattr(args, 'g'):
         g = args.g
@@ -38,7 +39,7 @@ for idx, (fn, args, name) in enumerate(e.prog.calls):
         key += ' dual' if args.dual else ''
     d = groups.setdefault(key, [0.0, 0, 0.0, 0.0])
     d[0] += ms; d[1] += 1
-    w = work.get(name, {}).get('per_call', {}).get(idx)
+    w = work.get(fam, {}).get('per_call', {}).get(idx)
     if w:
         if name in ('xm_conv', 'xm_wgrad'):
             d[2] += w
