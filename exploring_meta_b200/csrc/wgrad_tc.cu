@@ -1,19 +1,22 @@
 // wgrad_tc.cu -- tcgen05 / TMEM implementation of xm_wgrad for the 32-channel stride-1 layers.
 //
-// gW[tap][ci][co] = sum over positions q of g[q][co] * x[q + delta_tap][ci], on the same flattened
-// padded position sequence as conv_tc.cu (g is staged as zero at padding positions).  The reduction
-// dimension of the GEMM is the POSITION axis, so both operands are MN-major: position rows of 128 B
-// (= the 32 channels of one position, i.e. the natural NHWC row) in the 128B-swizzle/32B-base layout,
-// (the swizzle is a function of absolute address bits, so whole-row shifts of a descriptor start address or
-// of LBO address the same swizzled data).  A = X halo (M = 4 shifted copies x cin, K = 8 position rows)
-// and B = G (N = cout, K = 8 consecutive position rows).  The M = 128 rows of one tcgen05.mma (kind::tf32,
-// N = 32, K = 8) are FOUR 32-channel groups whose shared-memory stride is LBO; with LBO = 128 B = one position
-// row, group j is the x halo shifted by j positions -- i.e. the kernel-column taps kw = 0, 1, 2 (group 3 is
-// unused) of one kernel row kh come out of ONE instruction:
-//     D_kh[(kw, ci)][co] += sum_k x[row k0 + k + kh*Wp + kw][ci] * g[row k0 + k][co]
-// so a k-step costs 3 MMAs per expansion term instead of 9.  TMEM lane quarter kw holds tap (kh, kw), lane = ci,
-// column = co.  Two accumulator sets (2 x 3 x 32 columns) let the drain of tile i overlap the MMAs of tile i+1.
-// Accumulators are drained after every tile into fp32 registers with round-to-nearest adds (the tensor
+// gW[kh][kw][ci][co] = sum over positions q of g[q][co] * x[q + (kh-1)*Wp + (kw-1)][ci], on the same flattened
+// padded position sequence as conv_tc.cu.  The reduction dimension of the GEMM is the POSITION axis, so both
+// operands are MN-major: position rows of 128 B (= the 32 channels of one position, i.e. the natural NHWC row)
+// in the 128B-swizzle / 32B-base layout (the swizzle is a function of absolute address bits, so whole-row
+// shifts of a descriptor start address or of LBO address the same swizzled data).
+//
+// ALL NINE TAPS COME OUT OF ONE MMA (kind::tf32, M = 128, N = 96, K = 8 position rows).  With the substitution
+// q'' = q + (kh-1)*Wp the sum is  sum_q'' x[q'' + kw - 1][ci] * g[q'' - (kh-1)*Wp][co]  and
+//   * A = x tile: the four 32-lane groups of M are the x rows shifted by LBO = one position row, i.e. kw = 0, 1, 2
+//     (group 3 is unused);
+//   * B = g halo: the three 32-column groups of N are the g rows shifted by LBO = Wp position rows, i.e. kernel
+//     rows kh = 2, 1, 0;
+//   D[(kw, ci)][(2-kh, co)] += sum_k x[row k0 + k + kw][ci] * g[row k0 + k + (2-kh)*Wp][co].
+// A k-step therefore costs 3 MMAs (the 3xTF32 expansion terms) and 7 KB of shared-memory operand reads instead of
+// 27 MMAs / 135 KB for the one-tap-per-MMA form.  TMEM lane quarter kw / column block 2-kh holds tap (kh, kw),
+// lane = ci, column = co.  Two accumulator sets (2 x 96 columns) let the drain of tile i overlap the MMAs of tile
+// i+1.  Accumulators are drained after every tile into fp32 registers with round-to-nearest adds (the tensor
 // core's own accumulation truncates), and each CTA writes one partial block per task split;
 // wgrad_reduce_kernel (wgrad.cu) reduces the splits in double and applies the fused SGD / outer-recursion
 // epilogue.
@@ -21,15 +24,17 @@
 
 namespace xm {
 
-constexpr int WT_WORKERS = 256;
-constexpr int WT_THREADS = WT_WORKERS + 32;
+constexpr int WT_DRAINERS = 128;             // warps 0-3: warp kw < 3 drains TMEM lane quarter kw (warp 3 idles)
+constexpr int WT_PRODUCERS = 224;            // warps 4-10
+constexpr int WT_THREADS = WT_DRAINERS + WT_PRODUCERS + 32;   // + the MMA-issuing warp 11 (12 warps: 168 registers)
 constexpr int WT_TMEM_COLS = 256;            // 2 sets x 3 accumulators x 32 columns (192) -> next power of two
-constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 32, 1, 1);   // A and B MN-major
+constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 96, 1, 1);   // A and B MN-major, N = 3 kernel rows x 32 cout
 
 struct WgradTcK {
   int tasks, n, H, W, Hp, Wp, Q;
+  PosMap pm;
   int tiles_per_task, splits, npairs;
-  int R, xbuf;                        // staged x rows per tile, bytes of one x buffer (hi or lo)
+  int Rx, Rg, xbuf, gbuf;             // staged x / g rows per tile, bytes of one x / g buffer (hi or lo)
   int off_x0, off_x1, off_g0, off_g1, off_bar;   // shared-memory byte offsets
   const float* x[2];
   const float* g[2];
@@ -40,8 +45,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int task = blockIdx.y, split = blockIdx.x;
-  const int xset = p.xbuf;
-  constexpr int gset = 128 * 128;
+  const int xset = p.xbuf, gset = p.gbuf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
@@ -49,24 +53,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, WT_WORKERS);
+      mbar_init(bar_full + 8 * s, WT_PRODUCERS);
       mbar_init(bar_sfree + 8 * s, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tfree + 8 * s, 96);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WT_WORKERS / 32) {
+  if (warp == 11) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(WT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // rows past R (read only by the unused 4th lane group) must hold finite values
-  for (int i = tid; i < (xset - p.R * 128) / 16; i += WT_THREADS) {
+  // rows past Rx (read only by the unused 4th lane group) must hold finite values
+  for (int i = tid; i < (xset - p.Rx * 128) / 16; i += WT_THREADS) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t o = (size_t)p.R * 128 + (size_t)i * 16;
+    const size_t o = (size_t)p.Rx * 128 + (size_t)i * 16;
     *reinterpret_cast<float4*>(smem + p.off_x0 + o) = zero;
     *reinterpret_cast<float4*>(smem + p.off_x0 + xset + o) = zero;
     *reinterpret_cast<float4*>(smem + p.off_x1 + o) = zero;
@@ -80,102 +82,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 
   const int ntiles = (p.tiles_per_task - split + p.splits - 1) / p.splits;
   const int nunits = ntiles * p.npairs;
-  const int HpWp = p.Hp * p.Wp;
 
-  if (warp < WT_WORKERS / 32) {
-    // =============================== producers (+ warps 0-3: accumulator drain) =========================
-    const int c4 = tid & 7, jrow = tid >> 3;
-    float macc[3][32];                      // fp32 master accumulators: taps (kh, kw = warp), lane = ci, [co]
+  if (warp < 4) {
+    // ===================================== accumulator drain ============================================
+    // warp kw (0..2) owns TMEM lane quarter kw: lane = cin, column block j = 2 - kh of 32 cout columns.  The tile's
+    // accumulators are added (round-to-nearest) into fp32 master accumulators held in registers.
+    if (warp < 3) {
+      float macc[3][32];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) macc[a][c] = 0.f;
-
-    auto split_store = [](const float4& v, unsigned char* hi, unsigned char* lo) {
-      float4 h, l;
-      h.x = __uint_as_float(f2tf32(v.x)); l.x = v.x - h.x;
-      h.y = __uint_as_float(f2tf32(v.y)); l.y = v.y - h.y;
-      h.z = __uint_as_float(f2tf32(v.z)); l.z = v.z - h.z;
-      h.w = __uint_as_float(f2tf32(v.w)); l.w = v.w - h.w;
-      *reinterpret_cast<float4*>(hi) = h;
-      *reinterpret_cast<float4*>(lo) = l;
-    };
-
-    auto stage = [&](int u) {
-      const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
-      const int q0 = (split + it * p.splits) * 128;
-      const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * 32;
-      const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * 32;
-      // ---- x halo: rows j <-> positions q0 - Wp - 1 + j ------------------------------------------------
-      {
-        unsigned char* hi = smem + (s ? p.off_x1 : p.off_x0) + (c4 & 1) * 16;
-        unsigned char* lo = hi + xset;
-        const int ch = c4 >> 1;               // 32 B chunk of the 128 B row; swizzled with the row index
-        int q = q0 - p.Wp - 1 + jrow;
-        int img, r, c;
-        if (q >= 0) { img = q / HpWp; const int rem = q - img * HpWp; r = rem / p.Wp; c = rem - r * p.Wp; }
-        else { img = -1; r = p.Hp - 1; c = q + p.Wp; if (c < 0) { c += p.Wp; r -= 1; } }
-        for (int j0 = jrow; j0 < p.R; j0 += 128) {
-          float4 v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int j = j0 + 32 * k;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < p.R && img >= 0 && img < p.n && r >= 1 && c < p.W)
-              v[k] = __ldg(reinterpret_cast<const float4*>(X + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
-            c += 32;
-            while (c >= p.Wp) { c -= p.Wp; r += 1; }
-            while (r >= p.Hp) { r -= p.Hp; img += 1; }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int j = j0 + 32 * k;
-            if (j < p.R) {
-              const size_t o = (size_t)j * 128 + (size_t)((ch ^ (j & 3)) * 32);
-              split_store(v[k], hi + o, lo + o);
-            }
-          }
-        }
-      }
-      // ---- g tile: rows i <-> positions q0 + i, zero at padding positions ----------------------------------
-      {
-        unsigned char* hi = smem + (s ? p.off_g1 : p.off_g0) + (c4 & 1) * 16;
-        unsigned char* lo = hi + gset;
-        const int ch = c4 >> 1;
-        int q = q0 + jrow;
-        int img = q / HpWp;
-        const int rem = q - img * HpWp;
-        int r = rem / p.Wp, c = rem - r * p.Wp;
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (img < p.n && r >= 1 && c < p.W)
-            v[k] = __ldg(reinterpret_cast<const float4*>(G + (((long long)img * p.H + (r - 1)) * p.W + c) * 32) + c4);
-          c += 32;
-          while (c >= p.Wp) { c -= p.Wp; r += 1; }
-          while (r >= p.Hp) { r -= p.Hp; img += 1; }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = jrow + 32 * k;
-          const size_t o = (size_t)i * 128 + (size_t)((ch ^ (i & 3)) * 32);
-          split_store(v[k], hi + o, lo + o);
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
-    };
-
-    if (nunits > 0) stage(0);
-    for (int u = 0; u < nunits; ++u) {
-      if (u + 1 < nunits) {
-        if (u >= 1) mbar_wait(bar_sfree + 8 * ((u + 1) & 1), ((u - 1) >> 1) & 1);
-        stage(u + 1);
-      }
-      const int it = u / p.npairs;
-      if (warp < 3 && (u - it * p.npairs) == p.npairs - 1) {
-        // ---- drain the tile's accumulators: lane quarter = kw, lane = cin, 32 cout columns per kernel row ----
+        for (int c = 0; c < 32; ++c) macc[a][c] = 0.f;
+      for (int it = 0; it < ntiles; ++it) {
         const int set = it & 1;
         mbar_wait(bar_tfull + 8 * set, (it >> 1) & 1);
         tc_fence_after();
@@ -190,15 +108,90 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         tc_fence_before();
         mbar_arrive(bar_tfree + 8 * set);
       }
-    }
-    if (warp < 3) {
       float* P = p.partial + ((long long)task * p.splits + split) * 9 * 32 * 32;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        float4* dst = reinterpret_cast<float4*>(P + ((kh * 3 + warp) * 32 + lane) * 32);
+      for (int j = 0; j < 3; ++j) {
+        float4* dst = reinterpret_cast<float4*>(P + (((2 - j) * 3 + warp) * 32 + lane) * 32);   // tap (kh = 2-j, kw)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          dst[c] = make_float4(macc[kh][4 * c], macc[kh][4 * c + 1], macc[kh][4 * c + 2], macc[kh][4 * c + 3]);
+          dst[c] = make_float4(macc[j][4 * c], macc[j][4 * c + 1], macc[j][4 * c + 2], macc[j][4 * c + 3]);
+      }
+    }
+  } else if (warp < 11) {
+    // ========================================= producers =============================================
+    // A thread moves 8 channels (one 32 B swizzle chunk) of a row with one 256-bit load; rows of a unit:
+    //   x tile : j = jrow + PR*k (k < 3, j < Rx = 131)  <-> position q0 - 1 + j
+    //   g halo : i = jrow + PR*k (k < 4, i < Rg = 128 + 2*Wp)  <-> position q0 - Wp + i   (zero at padding positions)
+    // Register-level software pipeline: the loads of unit u+1 are issued before unit u is converted and
+    // stored (two register sets used alternately).
+    constexpr int PR = WT_PRODUCERS / 4;
+    const int ptid = tid - WT_DRAINERS;
+    const int c8 = ptid & 3, jrow = ptid >> 2;
+    struct Regs { float4 x[6]; float4 g[8]; };
+    auto issue = [&](int u, Regs& r) {
+      const int it = u / p.npairs, pair = u - it * p.npairs;
+      const int q0 = (split + it * p.splits) * 128;
+      const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
+      const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int j = jrow + PR * k;
+        const int px = j < p.Rx ? pos_to_pixel(p.pm, q0 - 1 + j) : -1;
+        r.x[2 * k] = r.x[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px >= 0) ldg256(X + (long long)px * 32, r.x[2 * k], r.x[2 * k + 1]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = jrow + PR * k;
+        const int px = i < p.Rg ? pos_to_pixel(p.pm, q0 - p.Wp + i) : -1;
+        r.g[2 * k] = r.g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px >= 0) ldg256(G + (long long)px * 32, r.g[2 * k], r.g[2 * k + 1]);
+      }
+    };
+    auto store = [&](int u, const Regs& r) {
+      const int s = u & 1;
+      if (u >= 2) mbar_wait(bar_sfree + 8 * s, ((u - 2) >> 1) & 1);     // MMAs of unit u-2 have read stage s
+      unsigned char* xhi = smem + (s ? p.off_x1 : p.off_x0);
+      unsigned char* ghi = smem + (s ? p.off_g1 : p.off_g0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int j = jrow + PR * k;
+        if (j < p.Rx) {
+          const size_t o = (size_t)j * 128 + (size_t)((c8 ^ (j & 3)) * 32);   // 32 B chunk swizzled with the row
+          float4 h, l;
+          split_tf32_fast(r.x[2 * k], h, l);
+          *reinterpret_cast<float4*>(xhi + o) = h;
+          *reinterpret_cast<float4*>(xhi + xset + o) = l;
+          split_tf32_fast(r.x[2 * k + 1], h, l);
+          *reinterpret_cast<float4*>(xhi + o + 16) = h;
+          *reinterpret_cast<float4*>(xhi + xset + o + 16) = l;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = jrow + PR * k;
+        if (i < p.Rg) {
+          const size_t o = (size_t)i * 128 + (size_t)((c8 ^ (i & 3)) * 32);
+          float4 h, l;
+          split_tf32_fast(r.g[2 * k], h, l);
+          *reinterpret_cast<float4*>(ghi + o) = h;
+          *reinterpret_cast<float4*>(ghi + gset + o) = l;
+          split_tf32_fast(r.g[2 * k + 1], h, l);
+          *reinterpret_cast<float4*>(ghi + o + 16) = h;
+          *reinterpret_cast<float4*>(ghi + gset + o + 16) = l;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    };
+    Regs ra, rb;
+    if (nunits > 0) issue(0, ra);
+    for (int u = 0; u < nunits; u += 2) {
+      if (u + 1 < nunits) issue(u + 1, rb);
+      store(u, ra);
+      if (u + 1 < nunits) {
+        if (u + 2 < nunits) issue(u + 2, ra);
+        store(u + 1, rb);
       }
     }
   } else {
@@ -210,26 +203,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       if (pair == 0 && it >= 2) mbar_wait(bar_tfree + 8 * set, ((it - 2) >> 1) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
-        // descriptor low words (start address | LBO); per MMA only the start field moves.  A = x halo with
-        // LBO = one position row (lane group j = halo shifted by j rows), B = g tile.
+        // descriptor low words (start address | LBO); per MMA only the start field moves.  A = x tile with
+        // LBO = one position row (lane group kw = tile shifted by kw rows), B = g halo with LBO = Wp position rows
+        // (column group j = halo shifted by j*Wp rows = kernel row 2 - j).
         const uint32_t x_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_x1 : p.off_x0)), 128u);
         const uint32_t x_lo0 = x_hi0 + (uint32_t)(xset >> 4);
-        const uint32_t g_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_g1 : p.off_g0)), 0u);
+        const uint32_t g_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_g1 : p.off_g0)), (uint32_t)p.Wp * 128u);
         const uint32_t g_lo0 = g_hi0 + (uint32_t)(gset >> 4);
         constexpr uint32_t dhi = umma_desc_hi(512u, 1u);            // SBO 512 B, 128B-swizzle / 32B-base layout
-        const uint32_t d0 = tmem_base + (uint32_t)(set * 96);
-        const uint32_t rowoff = (uint32_t)p.Wp * 8u;                // one kernel row = Wp position rows (16 B units)
+        const uint32_t d = tmem_base + (uint32_t)(set * 96);
+#pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t fresh = (pair == 0 && ks == 0) ? 0u : 1u;
           const uint32_t ko = (uint32_t)ks * 64u;                   // 8 position rows of 128 B per K step
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t ao = ko + (uint32_t)kh * rowoff;
-            const uint32_t d = d0 + (uint32_t)(kh * 32);
-            umma_tf32_lh(d, x_lo0 + ao, dhi, g_hi0 + ko, dhi, WT_IDESC, fresh);
-            umma_tf32_lh(d, x_hi0 + ao, dhi, g_lo0 + ko, dhi, WT_IDESC, 1u);
-            umma_tf32_lh(d, x_hi0 + ao, dhi, g_hi0 + ko, dhi, WT_IDESC, 1u);
-          }
+          umma_tf32_lh(d, x_lo0 + ko, dhi, g_hi0 + ko, dhi, WT_IDESC, fresh);
+          umma_tf32_lh(d, x_hi0 + ko, dhi, g_lo0 + ko, dhi, WT_IDESC, 1u);
+          umma_tf32_lh(d, x_hi0 + ko, dhi, g_hi0 + ko, dhi, WT_IDESC, 1u);
         }
         umma_commit(bar_sfree + 8 * s);
         if (pair == p.npairs - 1) umma_commit(bar_tfull + 8 * set);
@@ -240,7 +229,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == WT_WORKERS / 32) {
+  if (warp == 11) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WT_TMEM_COLS) : "memory");
   }
@@ -250,22 +239,23 @@ static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
   if (g.cin != 32 || g.cout != 32 || g.stride != 1) return false;
   p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
   p.Q = g.n * p.Hp * p.Wp;
+  p.pm = make_posmap(g.n, g.hin, g.win);
   p.tiles_per_task = (p.Q + 127) / 128;
-  p.R = 128 + 2 * p.Wp + 2;
-  p.xbuf = ((p.R + 1 + 7) & ~7) * 128;               // + the row the unused lane group reads; whole 1 KB units
-                                                     // keep every buffer 1024 B aligned
-  const int gbuf = 128 * 128;
+  p.Rx = 128 + 3;                                    // x tile + the three kw shifts
+  p.Rg = 128 + 2 * p.Wp;                             // g halo: kernel rows shift it by 0, Wp, 2*Wp rows
+  p.xbuf = ((p.Rx + 1 + 7) & ~7) * 128;              // + the row the unused lane group reads; whole 1 KB units
+  p.gbuf = ((p.Rg + 7) & ~7) * 128;                  // keep every buffer 1024 B aligned
   p.off_x0 = 0;
   p.off_g0 = p.off_x0 + 2 * p.xbuf;
-  p.off_x1 = p.off_g0 + 2 * gbuf;
+  p.off_x1 = p.off_g0 + 2 * p.gbuf;
   p.off_g1 = p.off_x1 + 2 * p.xbuf;
-  p.off_bar = p.off_g1 + 2 * gbuf;
+  p.off_bar = p.off_g1 + 2 * p.gbuf;
   smem = (size_t)p.off_bar + 8 * 8 + 16;
   int splits = num_sms() / g.tasks;
   if (splits < 1) splits = 1;
   if (splits > p.tiles_per_task) splits = p.tiles_per_task;
   p.splits = splits;
-  return smem <= 227 * 1024;
+  return smem <= 227 * 1024 && p.Rg <= WT_PRODUCERS;     // a producer thread stages <= 4 g rows per unit
 }
 
 // partial-buffer floats needed by the tcgen05 path for this geometry (0 if the shape is not covered)
