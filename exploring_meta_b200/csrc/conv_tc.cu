@@ -41,6 +41,14 @@ constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows 
 constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
 
+// 16-byte store, or (accumulate) a vector reduction into global memory: out += v, rounded like an fp32 add.
+__device__ __forceinline__ void put4(float* dst, const float4 v, int accumulate) {
+  if (accumulate)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else
+    *reinterpret_cast<float4*>(dst) = v;
+}
+
 struct ConvTcK {
   int tasks, n, H, W, Hp, Wp;        // source == output spatial dims (stride 1)
   PosMap pm;
@@ -279,14 +287,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       for (int half = 0; half < 2; ++half) {
         float (&acc)[16] = acc2[half];
         if (valid) {
-          if (p.accumulate) {
-            const float4* old4 = reinterpret_cast<const float4*>(p.out + o + half * 16);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 old = old4[k];
-              acc[4 * k] += old.x; acc[4 * k + 1] += old.y; acc[4 * k + 2] += old.z; acc[4 * k + 3] += old.w;
-            }
-          }
           if (p.stat_mode == XM_STAT_SUM_SQ) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -323,15 +323,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_NOSTORE
           if (acc[0] != 123456.f) continue;
 #endif
+          // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector
+          // reductions -- no read of the old value, so no load latency in the drain
           if (v_first) {
-            float4* d = reinterpret_cast<float4*>(p.out + o_first + col);
-            d[0] = odd ? make_float4(rx[0], rx[1], rx[2], rx[3]) : make_float4(acc[0], acc[1], acc[2], acc[3]);
-            d[2] = odd ? make_float4(ry[0], ry[1], ry[2], ry[3]) : make_float4(acc[8], acc[9], acc[10], acc[11]);
+            float* d = p.out + o_first + col;
+            put4(d, odd ? make_float4(rx[0], rx[1], rx[2], rx[3]) : make_float4(acc[0], acc[1], acc[2], acc[3]), p.accumulate);
+            put4(d + 8, odd ? make_float4(ry[0], ry[1], ry[2], ry[3]) : make_float4(acc[8], acc[9], acc[10], acc[11]), p.accumulate);
           }
           if (v_second) {
-            float4* d = reinterpret_cast<float4*>(p.out + o_second + col);
-            d[0] = odd ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(rx[0], rx[1], rx[2], rx[3]);
-            d[2] = odd ? make_float4(acc[12], acc[13], acc[14], acc[15]) : make_float4(ry[0], ry[1], ry[2], ry[3]);
+            float* d = p.out + o_second + col;
+            put4(d, odd ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(rx[0], rx[1], rx[2], rx[3]), p.accumulate);
+            put4(d + 8, odd ? make_float4(acc[12], acc[13], acc[14], acc[15]) : make_float4(ry[0], ry[1], ry[2], ry[3]), p.accumulate);
           }
         }
       }
@@ -437,6 +439,7 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
   if (g.cout != 32 || g.cin != 32 || g.stride != 1 || a->src_nchw) return 0;
+  if (a->src2 && a->stat_mode == XM_STAT_SUM_SQ) return 0;     // (sum of squares is not additive over the two passes)
   int R, plane_bytes;
   const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes);
   if (smem > 227 * 1024 || R > TC_PRODUCERS) return 0;      // each producer thread stages <= 4 rows per tile
@@ -464,7 +467,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     p.w = pair ? a->w2 : a->w1;
     p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
     p.accumulate = pair;                                   // second pair adds onto the first pass' output
-    p.stat_mode = (pair == npairs - 1) ? a->stat_mode : 0; // statistics of the final values only
+    p.stat_mode = a->stat_mode;                            // {sum v, sum v*aux} are linear: each pass adds its share
     conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
     if (int rc = launched("xm_conv(tcgen05)")) return rc;
   }
