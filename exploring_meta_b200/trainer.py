@@ -33,6 +33,39 @@ class _TrainerBase:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
 
+    # ---- input pipeline: host batch i+1 is copied to the device while batch i is being adapted -----------------
+    def stage(self, x_host, y_host):
+        """Starts the asynchronous host->device copy of a (pinned) batch into a staging slot on a side stream.
+        ``meta_step()`` without arguments then consumes the oldest staged batch.  Two slots: at most two batches
+        may be staged ahead of their ``meta_step``."""
+        e = self.engine
+        if getattr(self, '_stage', None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage = [(torch.empty_like(e.x), torch.empty_like(e.y)) for _ in range(2)]
+            self._staged = [torch.cuda.Event() for _ in range(2)]      # H2D into slot complete
+            self._consumed = [torch.cuda.Event() for _ in range(2)]    # slot copied into the engine inputs
+            for ev in self._consumed:
+                ev.record(torch.cuda.current_stream(self.device))
+            self._head = self._tail = 0
+        slot = self._tail % 2
+        self._tail += 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[slot])
+            self._stage[slot][0].copy_(x_host.view_as(e.x), non_blocking=True)
+            self._stage[slot][1].copy_(y_host, non_blocking=True)
+            self._staged[slot].record(self._copy_stream)
+
+    def _take_staged(self):
+        e = self.engine
+        assert getattr(self, '_stage', None) is not None and self._head < self._tail, 'no staged batch'
+        slot = self._head % 2
+        self._head += 1
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged[slot])
+        e.x.copy_(self._stage[slot][0], non_blocking=True)
+        e.y.copy_(self._stage[slot][1], non_blocking=True)
+        self._consumed[slot].record(cur)
+
     def _reduce_and_step(self, theta_all, global_tasks):
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
@@ -70,10 +103,15 @@ class MamlTrainer(_TrainerBase):
         assert flat.numel() == self.engine.P
         self.theta.copy_(flat)
 
-    def meta_step(self, x, y, track_running_stats=True):
+    def meta_step(self, x=None, y=None, track_running_stats=True):
+        """One meta-iteration.  ``x, y``: the shard's tasks (host or device tensors), or None to consume the batch
+        queued by ``stage()``."""
         e = self.engine
-        e.x.copy_(x, non_blocking=True)
-        e.y.copy_(y, non_blocking=True)
+        if x is None:
+            self._take_staged()
+        else:
+            e.x.copy_(x, non_blocking=True)
+            e.y.copy_(y, non_blocking=True)
         if self.use_graph and self.device.type == 'cuda':
             e.capture()
         e.launch()
@@ -113,10 +151,13 @@ class AnilTrainer(_TrainerBase):
         assert flat.numel() == self.theta_all.numel()
         self.theta_all.copy_(flat)
 
-    def meta_step(self, x, y):
+    def meta_step(self, x=None, y=None):
         e = self.engine
-        e.x.copy_(x, non_blocking=True)
-        e.y.copy_(y, non_blocking=True)
+        if x is None:
+            self._take_staged()
+        else:
+            e.x.copy_(x, non_blocking=True)
+            e.y.copy_(y, non_blocking=True)
         if self.use_graph and self.device.type == 'cuda':
             e.capture()
         e.launch()
