@@ -204,6 +204,21 @@ def program_work(engine):
                 if name == 'xm_conv' and a.stat_mode == 2:
                     by += 4.0 * g.tasks * g.n * g.hz * g.wz * g.cout          # aux (z) read by the tangent pass
                 w['bytes'] += by
+        elif name.startswith('xm_img'):
+            g = a.g
+            K = 9 * g.cin
+            x = 4.0 * g.tasks * g.n * g.cin * g.hin * g.win
+            pe = 1.0 * g.tasks * g.n * g.hp * g.wp * g.cout            # pooled elements
+            dense = 2.0 * g.tasks * g.n * g.hz * g.wz * K * g.cout     # the conv itself (CUDA-core FFMA2)
+            sparse = 2.0 * pe * K                                      # one 3x3xcin patch per pooling winner
+            fl, by = {'xm_img_gram': (2.0 * g.tasks * g.n * g.hz * g.wz * (K * (K + 1) / 2 + K), x),
+                      'xm_img_fwd': (dense, x + 9 * pe),               # writes p, zsel (fp32), sel (u8)
+                      'xm_img_dual_fwd': (dense, x + 13 * pe),         # reads zsel, sel; writes pdot, zdsel
+                      'xm_img_bwd': (sparse, x + 9 * pe),              # reads gp, zsel, sel
+                      'xm_img_dual_bwd': (sparse, x + 17 * pe)}[name]  # reads gp, gpdot, zsel, zdsel, sel
+            w['flops'] += fl
+            w['bytes'] += by
+            w['per_call'][idx] = by
         elif name.startswith('xm_bn'):
             g = a.g
             z = 4.0 * g.tasks * g.n * g.hz * g.wz * g.cout
@@ -349,11 +364,20 @@ def run_ours(args):
             fams[name] = fam
         line['kernels'] = fams
         def hbm_bound(name):
-            return name.startswith('xm_bn') or name.endswith(':image_layer')
+            return (name.startswith('xm_bn') or name.endswith(':image_layer')
+                    or name in ('xm_img_bwd', 'xm_img_dual_bwd'))
+
+        # exact-fp32 CUDA-core kernels (image-block forward conv, Gram matrix): bound by the FFMA / DFMA pipes
+        fp32_peak = 148 * 128 * 2 * (clocks.get('sm_max_mhz') or 1965.0) * 1e6 / 1e12
 
         for name, fam in fams.items():
             if hbm_bound(name) and 'gbs' in fam:
                 fam['roofline_frac'] = round(fam['gbs'] / peaks['hbm_gbs'], 4)
+            elif name in ('xm_img_fwd', 'xm_img_dual_fwd') and 'tflops' in fam:
+                fam['bound'] = 'fp32 CUDA cores (nominal %.1f TFLOP/s)' % fp32_peak
+                fam['roofline_frac'] = round(fam['tflops'] / fp32_peak, 4)
+            elif name == 'xm_img_gram':
+                fam['bound'] = 'fp64 CUDA cores'
             elif 'tflops' in fam:
                 fam['roofline_frac'] = round(fam['tflops'] / peaks['tensor_tflops'], 4)
         traffic = {}

@@ -52,6 +52,26 @@ class XmBnArgs(Structure):
                 ('scale', c_float), ('scratch', c_void_p)]
 
 
+class XmImgArgs(Structure):
+    _fields_ = [('g', XmBlockGeom), ('row0', c_int32), ('row_step', c_int32), ('rows_per_task', c_int32),
+                ('eps', c_float), ('scale', c_float),
+                ('x', c_void_p), ('gram', c_void_p),
+                ('w', c_void_p), ('w_task_stride', c_int64),
+                ('w_dot', c_void_p), ('wdot_task_stride', c_int64),
+                ('gamma', c_void_p), ('beta', c_void_p), ('gb_task_stride', c_int64),
+                ('gamma_dot', c_void_p), ('beta_dot', c_void_p), ('gbdot_task_stride', c_int64),
+                ('mean_invstd', c_void_p), ('call_stats', c_void_p), ('bwd_red', c_void_p),
+                ('dual_red', c_void_p),
+                ('p', c_void_p), ('zsel', c_void_p), ('sel', c_void_p),
+                ('pdot', c_void_p), ('zdsel', c_void_p),
+                ('gp', c_void_p), ('gpdot', c_void_p),
+                ('ssum', c_void_p), ('scratch', c_void_p),
+                ('out_w', c_void_p), ('out_b', c_void_p), ('out_gamma', c_void_p), ('out_beta', c_void_p),
+                ('out_task_stride', c_int64),
+                ('base_w', c_void_p), ('base_b', c_void_p), ('base_gamma', c_void_p), ('base_beta', c_void_p),
+                ('base_task_stride', c_int64)]
+
+
 class XmHeadArgs(Structure):
     _fields_ = [('tasks', c_int32), ('n', c_int32), ('ways', c_int32), ('c', c_int32), ('hw', c_int32),
                 ('mode', c_int32), ('dual', c_int32),
@@ -86,6 +106,14 @@ SYMBOLS = {
     'xm_bn_bwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
     'xm_bn_dual_fwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
     'xm_bn_dual_bwd': (c_int32, [POINTER(XmBnArgs), c_void_p]),
+    'xm_img_supported': (c_int32, [POINTER(XmBlockGeom)]),
+    'xm_img_gram_bytes': (c_int64, [POINTER(XmBlockGeom)]),
+    'xm_img_scratch_bytes': (c_int64, [POINTER(XmBlockGeom)]),
+    'xm_img_gram': (c_int32, [POINTER(XmImgArgs), c_void_p]),
+    'xm_img_fwd': (c_int32, [POINTER(XmImgArgs), c_void_p]),
+    'xm_img_bwd': (c_int32, [POINTER(XmImgArgs), c_void_p]),
+    'xm_img_dual_fwd': (c_int32, [POINTER(XmImgArgs), c_void_p]),
+    'xm_img_dual_bwd': (c_int32, [POINTER(XmImgArgs), c_void_p]),
     'xm_head': (c_int32, [POINTER(XmHeadArgs), c_void_p]),
     'xm_anil_head_scratch_bytes': (c_int64, [POINTER(XmAnilHeadArgs)]),
     'xm_anil_head': (c_int32, [POINTER(XmAnilHeadArgs), c_void_p]),

@@ -15,15 +15,18 @@ block is built once, and ``run()`` only replays the list -- so the whole iterati
 into a CUDA graph (``capture()``).
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib
 from ._lib import (XM_CONV_DGRAD, XM_CONV_FWD, XM_STAT_NONE, XM_STAT_SUM_AUX, XM_STAT_SUM_SQ,
-                   XmAnilHeadArgs, XmBlockGeom, XmBnArgs, XmConvArgs, XmHeadArgs, XmWgradArgs)
+                   XmAnilHeadArgs, XmBlockGeom, XmBnArgs, XmConvArgs, XmHeadArgs, XmImgArgs, XmWgradArgs)
 
 BN_EPS = 1e-5          # torch.nn.BatchNorm2d default, vision_models.py:168-174
 BN_MOMENTUM = 0.1
+# XM_NO_IMG_BLOCK=1 routes the first ConvBlock through the generic conv / bn / wgrad kernels (A/B comparison)
+_NO_IMG_BLOCK = os.environ.get('XM_NO_IMG_BLOCK', '') not in ('', '0')
 
 
 def _require_cuda(device):
@@ -103,11 +106,64 @@ class _EngineBase:
         wbytes = max(int(self.lib.xm_wgrad_scratch_bytes(ctypes.byref(self.geom(l, nmax)))) for l in range(L))
         self.wg_partial = torch.empty(max(wbytes, 4) // 4, dtype=torch.float32, device=self.device)
         del g0
+        # fused image block (xm_img_*): first ConvBlock without ever writing its pre-BN map (csrc/img_block.cu)
+        g = self.geom(0, nmax)
+        self.img = bool(self.lib.xm_img_supported(ctypes.byref(g))) and not _NO_IMG_BLOCK
+        if self.img:
+            K = 9 * g.cin
+            self.img_scratch = self._f64(int(self.lib.xm_img_scratch_bytes(ctypes.byref(g))) // 8)
+            self._gram_words = self.tasks * (K * K + K)
+
+    def _img_state(self, n, dual=False):
+        """Side buffers of one image-block call: winner values / positions and the sparse sums."""
+        st = {'zsel': self._f32(*self.pshape(0, n)),
+              'sel': torch.empty(self.pshape(0, n), dtype=torch.uint8, device=self.device),
+              'ssum': self._f64(self.tasks, self.C, 9 * self.spec.in_c + 3)}
+        return st
+
+    def _img_args(self, n, img, gram, theta, tstride):
+        o = self.offs
+        a = XmImgArgs()
+        a.g, a.eps = self.geom(0, n), BN_EPS
+        a.row0, a.row_step, a.rows_per_task = img
+        a.x, a.gram = _p(self.x), _p(gram)
+        a.w, a.w_task_stride = _p(theta, o[2]), tstride
+        a.gamma, a.beta, a.gb_task_stride = _p(theta, o[0]), _p(theta, o[1]), tstride
+        a.scratch = _p(self.img_scratch)
+        return a
+
+    def _emit_gram(self, prog, n, img, gram):
+        a = XmImgArgs()
+        a.g, a.eps = self.geom(0, n), BN_EPS
+        a.row0, a.row_step, a.rows_per_task = img
+        a.x, a.gram = _p(self.x), _p(gram)
+        prog.emit('xm_img_gram', a)
+
+    def _emit_img_fwd(self, prog, n, img, gram, theta, tstride, st, Pout, MI, call_stats):
+        a = self._img_args(n, img, gram, theta, tstride)
+        a.mean_invstd, a.call_stats, a.p = _p(MI), _p(call_stats), _p(Pout)
+        a.zsel, a.sel = _p(st['zsel']), _p(st['sel'])
+        prog.emit('xm_img_fwd', a)
+
+    def _emit_img_bwd(self, prog, n, img, gram, theta, tstride, st, GP, MI, BR, out, out_stride, base, base_stride, scale):
+        o = self.offs
+        a = self._img_args(n, img, gram, theta, tstride)
+        a.mean_invstd, a.bwd_red, a.gp = _p(MI), _p(BR), _p(GP)
+        a.zsel, a.sel, a.ssum = _p(st['zsel']), _p(st['sel']), _p(st['ssum'])
+        a.out_gamma, a.out_beta, a.out_w, a.out_b = _p(out, o[0]), _p(out, o[1]), _p(out, o[2]), _p(out, o[3])
+        a.out_task_stride = out_stride
+        a.base_gamma, a.base_beta = _p(base, o[0]), _p(base, o[1])
+        a.base_w, a.base_b = _p(base, o[2]), _p(base, o[3])
+        a.base_task_stride, a.scale = base_stride, scale
+        prog.emit('xm_img_bwd', a)
 
     # ---- emitters shared by the MAML and ANIL programs --------------------------------------
     def _emit_block_fwd(self, prog, l, n, src, img, theta, tstride, Z, Pout, MI, call_stats):
         """conv -> batch statistics -> normalise + ReLU + pool   (ConvBlock.forward, vision_models.py:188-193)."""
         o = self.offs
+        if l == 0 and self.img:
+            gram, st = Z
+            return self._emit_img_fwd(prog, n, img, gram, theta, tstride, st, Pout, MI, call_stats)
         a = XmConvArgs()
         a.g = self.geom(l, n)
         a.mode = XM_CONV_FWD
@@ -132,6 +188,10 @@ class _EngineBase:
                         out, out_stride, base, base_stride, scale):
         """BN/ReLU/pool backward -> dgrad -> wgrad, parameter gradients through the axpy epilogue."""
         o = self.offs
+        if l == 0 and self.img:
+            gram, st = Z
+            return self._emit_img_bwd(prog, n, img, gram, theta, tstride, st, GP, MI, BR, out, out_stride,
+                                      base, base_stride, scale)
         b = XmBnArgs()
         b.g, b.eps = self.geom(l, n), BN_EPS
         b.z, b.gp, b.mean_invstd, b.bwd_red, b.gz = _p(Z), _p(GP), _p(MI), _p(BR), _p(GZ)
@@ -233,19 +293,25 @@ class MamlEngine(_EngineBase):
         self.call_stats = torch.zeros((T + 1, L, B, 2, C), dtype=torch.float32, device=self.device)
         self._alloc_common(S)
         keep = T if mode == 'second' else 1           # per-step activations are only re-read by the dual sweep
-        self.Z = [[self._f32(*self.zshape(l, S)) for l in range(L)] for _ in range(keep)]
+        l0 = 1 if self.img else 0                     # the fused image block keeps (gram, winners) instead of z
+        if self.img:
+            self.gram_sup = self._f64(self._gram_words)
+            self.gram_qry = self._f64(self._gram_words)
+        self.Z = [[(self.gram_sup, self._img_state(S)) if l < l0 else self._f32(*self.zshape(l, S))
+                   for l in range(L)] for _ in range(keep)]
         self.Pa = [[self._f32(*self.pshape(l, S)) for l in range(L)] for _ in range(keep)]
         self.GP = [[self._f32(*self.pshape(l, S)) for l in range(L)] for _ in range(keep)]
         self.MI = [[self._f32(B, 2, C) for l in range(L)] for _ in range(keep)]
         self.BR = [[self._f32(B, 2, C) for l in range(L)] for _ in range(keep)]
         # temporaries: query pass (phase 2) and dual sweep (phase 3) share them
-        self.tZ = [self._f32(*self.zshape(l, S)) for l in range(L)]
+        self.tZ = [(self.gram_qry, self._img_state(S)) if l < l0 else self._f32(*self.zshape(l, S)) for l in range(L)]
+        self.tZD = self._f32(*self.pshape(0, S)) if (self.img and mode == 'second') else None   # zdot at the winners
         self.tP = [self._f32(*self.pshape(l, S)) for l in range(L)]
         self.tGP = [self._f32(*self.pshape(l, S)) for l in range(L)]
         self.tMI = [self._f32(B, 2, C) for l in range(L)]
         self.tBR = [self._f32(B, 2, C) for l in range(L)]
         self.tDR = [self._f32(B, 2, C) for l in range(L)]
-        zmax = max(self.tZ[l].numel() for l in range(L))
+        zmax = max([self.tZ[l].numel() for l in range(l0, L)] or [1])
         self.GZ = self._f32(zmax)
         self.GZdot = self._f32(zmax) if mode == 'second' else None
         self.bar = [self._f32(B, P), self._f32(B, P)] if mode != 'eval' else None
@@ -288,6 +354,9 @@ class MamlEngine(_EngineBase):
     def _build(self):
         prog, L, T, S, P = self.prog, self.spec.layers, self.steps, self.S, self.P
         sup, qry = (0, 2, self.rows), (1, 2, self.rows)
+        if self.img:                                   # Gram matrices of the support / query images, once
+            self._emit_gram(prog, S, sup, self.gram_sup)
+            self._emit_gram(prog, S, qry, self.gram_qry)
         # ---- phase 1: T inner steps on the support rows (core_functions/vision.py:9-13) ----------
         for t in range(T):
             k = t if self.mode == 'second' else 0
@@ -335,6 +404,15 @@ class MamlEngine(_EngineBase):
         th, ts = self._theta(t)
         Z, Pa, GP, MI, BR = self.Z[t], self.Pa[t], self.GP[t], self.MI[t], self.BR[t]
         for l in range(L):
+            if l == 0 and self.img:          # fused image block: zdot only at the winners, statistics from the Gram matrix
+                gram, st = Z[0]
+                a = self._img_args(S, sup, gram, th, ts)
+                a.w_dot, a.wdot_task_stride = _p(v, o[2]), P
+                a.gamma_dot, a.beta_dot, a.gbdot_task_stride = _p(v, o[0]), _p(v, o[1]), P
+                a.mean_invstd, a.dual_red = _p(MI[0]), _p(self.tDR[0])
+                a.zsel, a.sel, a.pdot, a.zdsel = _p(st['zsel']), _p(st['sel']), _p(self.tP[0]), _p(self.tZD)
+                prog.emit('xm_img_dual_fwd', a)
+                continue
             a = XmConvArgs()
             a.g, a.mode, a.stat_mode = self.geom(l, S), XM_CONV_FWD, XM_STAT_SUM_AUX
             if l == 0:                       # images carry no tangent: zdot = conv(x, Wdot)
@@ -357,6 +435,20 @@ class MamlEngine(_EngineBase):
         self._emit_head(prog, S, Pa[L - 1], th, ts, 0, self.tGP[L - 1], out, P, v, P, -self.lr,
                         dual=(self.tP[L - 1], v))
         for l in reversed(range(L)):
+            if l == 0 and self.img:
+                gram, st = Z[0]
+                a = self._img_args(S, sup, gram, th, ts)
+                a.w_dot, a.wdot_task_stride = _p(v, o[2]), P
+                a.gamma_dot, a.beta_dot, a.gbdot_task_stride = _p(v, o[0]), _p(v, o[1]), P
+                a.mean_invstd, a.bwd_red, a.dual_red = _p(MI[0]), _p(BR[0]), _p(self.tDR[0])
+                a.gp, a.gpdot = _p(GP[0]), _p(self.tGP[0])
+                a.zsel, a.sel, a.zdsel, a.ssum = _p(st['zsel']), _p(st['sel']), _p(self.tZD), _p(st['ssum'])
+                a.out_gamma, a.out_beta, a.out_w, a.out_b = _p(out, o[0]), _p(out, o[1]), _p(out, o[2]), _p(out, o[3])
+                a.out_task_stride = P
+                a.base_gamma, a.base_beta, a.base_w, a.base_b = _p(v, o[0]), _p(v, o[1]), _p(v, o[2]), _p(v, o[3])
+                a.base_task_stride, a.scale = P, -self.lr
+                prog.emit('xm_img_dual_bwd', a)
+                continue
             b = XmBnArgs()
             b.g, b.eps = self.geom(l, S), BN_EPS
             b.z, b.zdot, b.gp, b.gpdot = _p(Z[l]), _p(self.tZ[l]), _p(GP[l]), _p(self.tGP[l])
@@ -445,12 +537,15 @@ class AnilEngine(_EngineBase):
         self.correct = torch.zeros(B, dtype=torch.int32, device=self.device)
         self.call_stats = torch.zeros((L, B, 2, C), dtype=torch.float32, device=self.device)
         self._alloc_common(R)
-        self.Z = [self._f32(*self.zshape(l, R)) for l in range(L)]
+        l0 = 1 if self.img else 0
+        if self.img:
+            self.gram = self._f64(self._gram_words)
+        self.Z = [(self.gram, self._img_state(R)) if l < l0 else self._f32(*self.zshape(l, R)) for l in range(L)]
         self.Pa = [self._f32(*self.pshape(l, R)) for l in range(L)]
         self.GP = [self._f32(*self.pshape(l, R)) for l in range(L)]
         self.MI = [self._f32(B, 2, C) for l in range(L)]
         self.BR = [self._f32(B, 2, C) for l in range(L)]
-        self.GZ = self._f32(max(z.numel() for z in self.Z))
+        self.GZ = self._f32(max([self.Z[l].numel() for l in range(l0, L)] or [1]))
         self.task_grad = self._f32(B, P)
         self.task_head_grad = self._f32(B, self.PH)
         self.prog = _Program(self.lib)
@@ -459,6 +554,8 @@ class AnilEngine(_EngineBase):
     def _build(self):
         prog, L, B, P, R = self.prog, self.spec.layers, self.tasks, self.P, self.rows
         rows = (0, 1, R)
+        if self.img:
+            self._emit_gram(prog, R, rows, self.gram)
         for l in range(L):
             self._emit_block_fwd(prog, l, R, self.Pa[l - 1] if l else None, rows, self.theta, 0,
                                  self.Z[l], self.Pa[l], self.MI[l], self.call_stats[l])

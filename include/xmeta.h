@@ -136,6 +136,56 @@ int xm_bn_dual_fwd(const XmBnArgs* a, void* stream);
  * writes gz (recomputed; NULL = not needed), gzdot, out_gamma/out_beta = base + scale * tangent of (g_gamma, g_beta) */
 int xm_bn_dual_bwd(const XmBnArgs* a, void* stream);
 
+/* Image block: the FIRST ConvBlock of the network (core_functions/vision_models.py:135-139 -- conv3x3 on the user
+ * images, cin <= 4, then BN(train) + ReLU + MaxPool 2x2) as one fused unit that never writes the pre-BN map z.
+ * The block input is constant over the inner loop and carries no gradient, so every dense reduction over z is a
+ * closed form in the per-task Gram matrix of the im2col'd images (xm_img_gram, once per meta-iteration), and the
+ * rest of the backward only visits the pooling winners (derivation: exploring_meta_b200/csrc/img_block.cu).
+ * Covered geometry: xm_img_supported(); everything else goes through xm_conv / xm_bn_* / xm_wgrad.
+ * K = 9*cin, weight index k = ci*9 + kh*3 + kw (PyTorch's [cout][cin][3][3]).  Side buffers:
+ *   gram  [tasks][K*K + K] double : G = X^T X, then sx = X^T 1           (xm_img_gram_bytes)
+ *   zsel  [t][n][hp][wp][cout]    : z at the pooling winner (0 where the ReLU is dead)
+ *   sel   [t][n][hp][wp][cout] u8 : winner position dy*2+dx inside the window, 255 = ReLU-dead
+ *   zdsel like zsel               : tangent of z at the winner
+ *   ssum  [tasks][cout][K+3] double: sparse sums {S[K], sum g, sum g*xhat, -} of xm_img_bwd, read by xm_img_dual_bwd
+ *   scratch >= xm_img_scratch_bytes
+ * mean_invstd / call_stats / bwd_red / dual_red, the axpy epilogue and the row selection are as in XmBnArgs /
+ * XmConvArgs.  Replaces, for this block: conv2d + native_batch_norm + relu + max_pool2d_with_indices, their backward
+ * and double-backward ops (vision/maml_vision.py:112) and maml_update's `p + (-lr*g)`. */
+typedef struct XmImgArgs {
+  XmBlockGeom g;
+  int32_t row0, row_step, rows_per_task;
+  float eps, scale;
+  const float* x;                               /* user images [tasks][rows_per_task][cin][hin][win]      */
+  double* gram;
+  const float* w; int64_t w_task_stride;
+  const float* w_dot; int64_t wdot_task_stride;
+  const float* gamma; const float* beta; int64_t gb_task_stride;
+  const float* gamma_dot; const float* beta_dot; int64_t gbdot_task_stride;
+  float* mean_invstd; float* call_stats; float* bwd_red; float* dual_red;
+  float* p; float* zsel; uint8_t* sel;
+  float* pdot; float* zdsel;
+  const float* gp; const float* gpdot;          /* cotangent of p and its tangent (gpdot NULL = 0)         */
+  double* ssum;
+  double* scratch;
+  float* out_w; float* out_b; float* out_gamma; float* out_beta; int64_t out_task_stride;
+  const float* base_w; const float* base_b; const float* base_gamma; const float* base_beta; int64_t base_task_stride;
+} XmImgArgs;
+int xm_img_supported(const XmBlockGeom* g);
+int64_t xm_img_gram_bytes(const XmBlockGeom* g);
+int64_t xm_img_scratch_bytes(const XmBlockGeom* g);
+/* reads x                                              writes gram                                          */
+int xm_img_gram(const XmImgArgs* a, void* stream);
+/* reads x, gram, w, gamma, beta                        writes p, zsel, sel, mean_invstd, call_stats(opt)    */
+int xm_img_fwd(const XmImgArgs* a, void* stream);
+/* reads x, gram, w, gamma, mean_invstd, gp, zsel, sel  writes bwd_red, ssum(opt), out_* = base + scale*grad  */
+int xm_img_bwd(const XmImgArgs* a, void* stream);
+/* reads x, gram, w, w_dot, gamma(+dot), beta_dot, mean_invstd, zsel, sel     writes pdot, zdsel, dual_red     */
+int xm_img_dual_fwd(const XmImgArgs* a, void* stream);
+/* reads x, gram, w, w_dot, gamma(+dot), mean_invstd, bwd_red, dual_red, ssum, gp, gpdot, zsel, zdsel, sel
+ * writes out_* = base + scale * tangent of (gW, gb, g_gamma, g_beta)                                         */
+int xm_img_dual_bwd(const XmImgArgs* a, void* stream);
+
 /* xm_head: classifier head on block-4 features, one CTA per task, forward + loss + backward fused.
  *   mode 0 (MiniImagenetCNN.forward, vision_models.py:107-110): X = flatten in NCHW order, D = c*hw
  *   mode 1 (OmniglotCNN.forward :51-55):                        X = mean over hw,           D = c

@@ -13,7 +13,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-_NP = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
+_NP = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32,
+       torch.uint8: np.uint8}
 
 
 def view(addr, shape, dtype=torch.float32):
@@ -291,6 +292,184 @@ class EmulatedLib:
         cnt = g.n * g.hz * g.wz
         axpy_out(a.out_gamma, a.out_task_stride, a.base_gamma, a.base_task_stride, a.scale, g.tasks, (e2 + q) * cnt)
         axpy_out(a.out_beta, a.out_task_stride, a.base_beta, a.base_task_stride, a.scale, g.tasks, e1 * cnt)
+        return 0
+
+    # ------------------------------------------------------------------ image block (fused first ConvBlock)
+    # Contract evaluated the DENSE way (conv -> z -> BN -> pool and back); the CUDA kernels reach the same
+    # numbers through the Gram-matrix closed forms of exploring_meta_b200/csrc/img_block.cu.
+    @staticmethod
+    def _img_ok(g):
+        return (1 <= g.cin <= 4 and g.stride == 1 and g.pool == 1 and g.hz % 2 == 0 and g.wz % 2 == 0
+                and g.cout % 32 == 0)
+
+    def xm_img_supported(self, ref):
+        return 1 if self._img_ok(self._args(ref)) else 0
+
+    def xm_img_gram_bytes(self, ref):
+        g = self._args(ref)
+        K = 9 * g.cin
+        return g.tasks * (K * K + K) * 8
+
+    def xm_img_scratch_bytes(self, ref):
+        g = self._args(ref)
+        return g.tasks * g.cout * (9 * g.cin + 3) * 8
+
+    def _img_x(self, a):
+        return _block_input(a.x, a.g, 1, a.row0, a.row_step, a.rows_per_task)       # [tasks, n, cin, H, W]
+
+    def _img_conv(self, a, waddr, wstride):
+        g = a.g
+        x = self._img_x(a)
+        W = param(waddr, wstride, g.tasks, (g.cout, g.cin, 3, 3))
+        z = torch.stack([F.conv2d(x[t], W[t], None, stride=1, padding=1) for t in range(g.tasks)])
+        return z.permute(0, 1, 3, 4, 2).contiguous()                                # NHWC
+
+    def _img_selmask(self, a):
+        """0/1 mask over z positions decoded from the stored winner indices."""
+        g = a.g
+        sel = view(a.sel, (g.tasks, g.n, g.hp, g.wp, g.cout), torch.uint8).long()
+        m = torch.zeros(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout)
+        for d in range(4):
+            m[:, :, :, d >> 1, :, d & 1, :] = (sel == d).float()
+        return m.reshape(g.tasks, g.n, g.hz, g.wz, g.cout)
+
+    def xm_img_gram(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        K = 9 * g.cin
+        x = self._img_x(a).double()
+        out = view(a.gram, (g.tasks, K * K + K), torch.float64)
+        for t in range(g.tasks):
+            cols = F.unfold(x[t], 3, padding=1)                  # [n, K, H*W], k = ci*9 + kh*3 + kw
+            X = cols.permute(1, 0, 2).reshape(K, -1)
+            out[t, :K * K] = (X @ X.t()).reshape(-1)
+            out[t, K * K:] = X.sum(1)
+        return 0
+
+    def xm_img_fwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        z = self._img_conv(a, a.w, a.w_task_stride)
+        cnt = g.n * g.hz * g.wz
+        mean = z.double().mean(dim=(1, 2, 3))
+        var = (z.double() ** 2).mean(dim=(1, 2, 3)) - mean * mean
+        var = var.clamp_min(0)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        mi[:, 0] = mean.float()
+        mi[:, 1] = (1.0 / torch.sqrt(var + a.eps)).float()
+        if a.call_stats:
+            cs = view(a.call_stats, (g.tasks, 2, g.cout))
+            cs[:, 0] = mean.float()
+            cs[:, 1] = (var * (cnt / max(cnt - 1, 1))).float()
+        gamma = param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,))
+        beta = param(a.beta, a.gb_task_stride, g.tasks, (g.cout,))
+        xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
+        y = _bc(gamma) * xhat + _bc(beta)
+        yw = y.reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).permute(0, 1, 2, 4, 6, 3, 5).reshape(
+            g.tasks, g.n, g.hp, g.wp, g.cout, 4)
+        zw = z.reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).permute(0, 1, 2, 4, 6, 3, 5).reshape(
+            g.tasks, g.n, g.hp, g.wp, g.cout, 4)
+        ymax, idx = yw.max(dim=-1)                               # first maximum in row-major window order
+        # torch.max returns the first index among equal maxima on CPU
+        on = ymax > 0
+        view(a.p, ymax.shape).copy_(torch.where(on, ymax, torch.zeros_like(ymax)))
+        view(a.zsel, ymax.shape).copy_(torch.where(on, zw.gather(-1, idx[..., None])[..., 0], torch.zeros_like(ymax)))
+        view(a.sel, ymax.shape, torch.uint8).copy_(torch.where(on, idx, torch.full_like(idx, 255)).to(torch.uint8))
+        return 0
+
+    def _img_bwd_common(self, a):
+        g = a.g
+        z = self._img_conv(a, a.w, a.w_task_stride)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        gamma = param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,))
+        xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
+        sel = self._img_selmask(a)
+        gbn = sel * _up(view(a.gp, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
+        return z, mi, gamma, xhat, sel, gbn
+
+    def _img_wgrad(self, a, gz):
+        g = a.g
+        x = self._img_x(a)
+        gzn = gz.permute(0, 1, 4, 2, 3).contiguous()
+        return torch.stack([torch.nn.grad.conv2d_weight(x[t], (g.cout, g.cin, 3, 3), gzn[t], stride=1, padding=1)
+                            for t in range(g.tasks)])
+
+    def _img_outputs(self, a, gW, ggamma, gbeta):
+        g = a.g
+        axpy_out(a.out_w, a.out_task_stride, a.base_w, a.base_task_stride, a.scale, g.tasks, gW)
+        axpy_out(a.out_b, a.out_task_stride, a.base_b, a.base_task_stride, 0.0, g.tasks, torch.zeros(g.tasks, g.cout))
+        axpy_out(a.out_gamma, a.out_task_stride, a.base_gamma, a.base_task_stride, a.scale, g.tasks, ggamma)
+        axpy_out(a.out_beta, a.out_task_stride, a.base_beta, a.base_task_stride, a.scale, g.tasks, gbeta)
+
+    def xm_img_bwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 2
+        z, mi, gamma, xhat, sel, gbn = self._img_bwd_common(a)
+        m1, m2 = _mean(gbn), _mean(gbn * xhat)
+        if a.bwd_red:
+            br = view(a.bwd_red, (g.tasks, 2, g.cout))
+            br[:, 0], br[:, 1] = m1, m2
+        cnt = g.n * g.hz * g.wz
+        if a.ssum:
+            K = 9 * g.cin
+            ss = view(a.ssum, (g.tasks, g.cout, K + 3), torch.float64)
+            ss[:, :, :K] = self._img_wgrad(a, gbn).double().reshape(g.tasks, g.cout, K)
+            ss[:, :, K] = gbn.double().sum(dim=(1, 2, 3))
+            ss[:, :, K + 1] = (gbn.double() * xhat.double()).sum(dim=(1, 2, 3))
+            ss[:, :, K + 2] = 0
+        gz = _bc(gamma * mi[:, 1]) * (gbn - _bc(m1) - xhat * _bc(m2))
+        self._img_outputs(a, self._img_wgrad(a, gz), m2 * cnt, m1 * cnt)
+        return 0
+
+    def xm_img_dual_fwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 1
+        z = self._img_conv(a, a.w, a.w_task_stride)
+        zd = self._img_conv(a, a.w_dot, a.wdot_task_stride)
+        mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+        mean, r = mi[:, 0].double(), mi[:, 1].double()
+        d1 = zd.double().mean(dim=(1, 2, 3))
+        d2 = r * ((zd.double() * z.double()).mean(dim=(1, 2, 3)) - mean * d1)
+        dr = view(a.dual_red, (g.tasks, 2, g.cout))
+        dr[:, 0], dr[:, 1] = d1.float(), d2.float()
+        gamma = param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,))
+        gd = param(a.gamma_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        bd = param(a.beta_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
+        xhd = _bc(mi[:, 1]) * (zd - _bc(dr[:, 0]) - xhat * _bc(dr[:, 1]))
+        yd = _bc(gd) * xhat + _bc(gamma) * xhd + _bc(bd)
+        sel = self._img_selmask(a)
+        pd = _down(sel * yd, g)
+        view(a.pdot, pd.shape).copy_(pd)
+        view(a.zdsel, pd.shape).copy_(_down(sel * zd, g))
+        return 0
+
+    def xm_img_dual_bwd(self, ref, stream):
+        a = self._args(ref)
+        g = a.g
+        self.launches += 2
+        z, mi, gamma, xhat, sel, gbn = self._img_bwd_common(a)
+        zd = self._img_conv(a, a.w_dot, a.wdot_task_stride)
+        br = view(a.bwd_red, (g.tasks, 2, g.cout))
+        dr = view(a.dual_red, (g.tasks, 2, g.cout))
+        gd = param(a.gamma_dot, a.gbdot_task_stride, g.tasks, (g.cout,))
+        if a.gpdot:
+            gbnd = sel * _up(view(a.gpdot, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
+        else:
+            gbnd = torch.zeros_like(gbn)
+        r, m1, m2, d1, d2 = mi[:, 1], br[:, 0], br[:, 1], dr[:, 0], dr[:, 1]
+        e1, e2, e3 = _mean(gbnd), _mean(gbnd * xhat), _mean(gbn * zd)
+        q = r * (e3 - d1 * m1 - d2 * m2)
+        rdot = -r * r * d2
+        xhd = _bc(r) * (zd - _bc(d1) - xhat * _bc(d2))
+        proj = gbn - _bc(m1) - xhat * _bc(m2)
+        gzd = _bc(gd * r + gamma * rdot) * proj + _bc(gamma * r) * (gbnd - _bc(e1) - xhd * _bc(m2) - xhat * _bc(e2 + q))
+        cnt = g.n * g.hz * g.wz
+        self._img_outputs(a, self._img_wgrad(a, gzd), (e2 + q) * cnt, e1 * cnt)
         return 0
 
     # ------------------------------------------------------------------ heads

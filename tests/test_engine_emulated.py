@@ -20,6 +20,7 @@ CASES = [
     (pspec.NetSpec(3, 12, 12, 8, 3, 2, True, 'flatten'), 2, 2, 0.1, 3),
     (pspec.NetSpec(1, 14, 14, 8, 4, 3, False, 'mean'), 1, 1, 0.4, 2),
     (pspec.NetSpec(2, 21, 21, 4, 2, 4, True, 'flatten'), 1, 3, 0.05, 2),   # odd sizes: floor pooling
+    (pspec.NetSpec(3, 12, 16, 32, 3, 2, True, 'flatten'), 2, 2, 0.1, 2),   # fused image-block path (xm_img_*)
 ]
 
 
@@ -42,8 +43,9 @@ def test_maml_second_order_matches_oracle(emulated_lib, spec, shots, steps, lr, 
         assert mo.rel_l2(e.theta_steps[steps - 1, t][mask], th[mask]) < 1e-4
 
 
-def test_maml_first_order_and_eval(emulated_lib):
-    spec, shots, steps, lr, tasks = CASES[0]
+@pytest.mark.parametrize('case', [0, 3])
+def test_maml_first_order_and_eval(emulated_lib, case):
+    spec, shots, steps, lr, tasks = CASES[case]
     ospec = _ospec(spec)
     params = mo.init_params(ospec, seed=5)
     X, Y = make_tasks(tasks, spec.ways, shots, (spec.in_c, spec.in_h, spec.in_w), seed=2)
@@ -78,9 +80,21 @@ def test_bn_running_stats(emulated_lib):
         assert torch.allclose(rv[l], rv_ref[l], rtol=1e-4, atol=1e-5)
 
 
+def test_image_block_path_is_taken(emulated_lib):
+    spec, shots, steps, lr, tasks = CASES[3]
+    e = eng.MamlEngine(spec, tasks, shots, steps, lr, mode='second', device='cpu')
+    names = [name for _fn, _a, name in e.prog.calls]
+    assert e.img and names.count('xm_img_gram') == 2
+    assert names.count('xm_img_fwd') == steps + 1 and names.count('xm_img_bwd') == steps + 1
+    assert names.count('xm_img_dual_fwd') == steps and names.count('xm_img_dual_bwd') == steps
+    e8 = eng.MamlEngine(CASES[0][0], tasks, shots, steps, lr, mode='second', device='cpu')
+    assert not e8.img and not any(n.startswith('xm_img') for _f, _a, n in e8.prog.calls)
+
+
 @pytest.mark.parametrize('first_order', [False, True])
-def test_anil_matches_oracle(emulated_lib, first_order):
-    spec = pspec.NetSpec(3, 12, 12, 8, 3, 2, True, 'none')
+@pytest.mark.parametrize('hidden', [8, 32])
+def test_anil_matches_oracle(emulated_lib, first_order, hidden):
+    spec = pspec.NetSpec(3, 12, 12, hidden, 3, 2, True, 'none')
     shots, steps, lr, tasks = 2, 2, 0.3, 3
     ospec = _ospec(spec)
     body = mo.init_params(ospec, seed=7, with_head=False)
