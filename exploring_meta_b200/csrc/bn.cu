@@ -198,9 +198,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnK k) {
   Chan<VEC> ch;
   load_gb<VEC>(k, task, c0, ch);
   load_mi<VEC>(k, task, c0, ch);
+  // fp32 partials over short runs (<= 16 windows), folded into double: the double pipe (and its conversions)
+  // would otherwise bound this pass instead of HBM
   double acc[2][VEC];
+  float fa[2][VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) acc[0][v] = acc[1][v] = 0.0;
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = acc[1][v] = 0.0; fa[0][v] = fa[1][v] = 0.f; }
+  int run = 0;
   const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // host sets wh/ww = hp/wp here
   for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
     const Window w = make_window(k, task, px, c0);
@@ -219,10 +223,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnK k) {
 #pragma unroll
         for (int d = 1; d < 4; ++d) if (sel[v] == d) zs = z[d][v];
         const float xhat = (zs - ch.mean[v]) * ch.r[v];
-        acc[0][v] += (double)gp[v];
-        acc[1][v] += (double)gp[v] * (double)xhat;
+        fa[0][v] += gp[v];
+        fa[1][v] = fmaf(gp[v], xhat, fa[1][v]);
       }
+    if ((++run & 15) == 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        acc[0][v] += (double)fa[0][v]; acc[1][v] += (double)fa[1][v];
+        fa[0][v] = fa[1][v] = 0.f;
+      }
+    }
   }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] += (double)fa[0][v]; acc[1][v] += (double)fa[1][v]; }
   flush_stats<VEC, 2>(k, task, c0, acc, sh);
 }
 
@@ -345,8 +358,10 @@ __global__ void __launch_bounds__(256) bn_dual_bwd_reduce_kernel(const BnK k) {
   load_gb<VEC>(k, task, c0, ch);
   load_mi<VEC>(k, task, c0, ch);
   double acc[3][VEC];
+  float fa[3][VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) acc[0][v] = acc[1][v] = acc[2][v] = 0.0;
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = acc[1][v] = acc[2][v] = 0.0; fa[0][v] = fa[1][v] = fa[2][v] = 0.f; }
+  int run = 0;
   const int npx = k.n * k.wh * k.ww, pslots = blockDim.x / cq;     // pooled windows
   for (int px = blockIdx.x * pslots + threadIdx.x / cq; px < npx; px += gridDim.x * pslots) {
     const Window w = make_window(k, task, px, c0);
@@ -368,11 +383,20 @@ __global__ void __launch_bounds__(256) bn_dual_bwd_reduce_kernel(const BnK k) {
 #pragma unroll
         for (int d = 1; d < 4; ++d) if (sel[v] == d) { zs = z[d][v]; zds = zd[d][v]; }
         const float xhat = (zs - ch.mean[v]) * ch.r[v];
-        acc[0][v] += (double)gpd[v];
-        acc[1][v] += (double)gpd[v] * (double)xhat;
-        acc[2][v] += (double)gp[v] * (double)zds;
+        fa[0][v] += gpd[v];
+        fa[1][v] = fmaf(gpd[v], xhat, fa[1][v]);
+        fa[2][v] = fmaf(gp[v], zds, fa[2][v]);
       }
+    if ((++run & 15) == 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        acc[0][v] += (double)fa[0][v]; acc[1][v] += (double)fa[1][v]; acc[2][v] += (double)fa[2][v];
+        fa[0][v] = fa[1][v] = fa[2][v] = 0.f;
+      }
+    }
   }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] += (double)fa[0][v]; acc[1][v] += (double)fa[1][v]; acc[2][v] += (double)fa[2][v]; }
   flush_stats<VEC, 3>(k, task, c0, acc, sh);
 }
 

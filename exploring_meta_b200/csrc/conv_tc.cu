@@ -210,15 +210,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t0 = clock64();
 #endif
+      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE + row;
+      const int px = row < TC_TILE ? pos_to_pixel(p.pm, q) : -1;
+      const bool valid = px >= 0;
+      const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * 32;
+      // tangent statistics multiply by one 128 B aux row per accumulator row: pull it into L1 while the warp waits
+      // for the accumulators, so the loads in the epilogue do not expose HBM latency inside the drain
+      if (p.stat_mode == XM_STAT_SUM_AUX && valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.aux + o));
       mbar_wait(bar_tfull + 8 * s, (it >> 1) & 1);
 #ifdef XM_TC_TIMING
       t_wait += clock64() - t0; t0 = clock64();
 #endif
       tc_fence_after();
-      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE + row;
-      const int px = row < TC_TILE ? pos_to_pixel(p.pm, q) : -1;
-      const bool valid = px >= 0;
-      const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * 32;
       const long long o_pair = __shfl_xor_sync(0xffffffffu, o, 1);
       const bool v_pair = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 192);
@@ -277,9 +280,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
-          const float* xn = xch + ((((it & 1) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16;
+          // (16-byte loads, all issued before the first use: one shared-memory round trip instead of 48)
+          const float4* xn = reinterpret_cast<const float4*>(xch + ((((it & 1) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
+          float4 a[4], b[4];
+          const int oa = lane == 31 ? 0 : 4;                     // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
 #pragma unroll
-          for (int k = 0; k < 16; ++k) acc2[half][k] += lane == 31 ? xn[k] + xn[32 + k] : xn[16 + k];
+          for (int k = 0; k < 4; ++k) { a[k] = xn[oa + k]; b[k] = xn[8 + k]; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 z = lane == 31 ? b[k] : make_float4(0.f, 0.f, 0.f, 0.f);   // lane 31 adds kw=2 of row +2 (lane 1)
+            acc2[half][4 * k] += a[k].x + z.x; acc2[half][4 * k + 1] += a[k].y + z.y;
+            acc2[half][4 * k + 2] += a[k].z + z.z; acc2[half][4 * k + 3] += a[k].w + z.w;
+          }
         }
       }
       // ---- epilogue of both halves: (accumulate), statistics, paired full-sector stores --------------------------

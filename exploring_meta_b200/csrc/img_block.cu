@@ -462,94 +462,94 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// Closed-form tails, one thread per (task, channel), all in double.
-template <int CIN>
-__global__ void img_bwd_finalize_kernel(const ImgK p) {
+// Closed-form tails, one CTA per task, all in double.  G, sx and the weights are staged in shared memory once; the
+// matrix-vector products G w (and G wd) are spread over (channel, k) pairs, then one thread per channel finishes.
+template <int CIN, int DUAL>
+__global__ void __launch_bounds__(256) img_finalize_kernel(const ImgK p) {
   constexpr int K = 9 * CIN, NA = K + 3;
-  const int task = blockIdx.x, co = threadIdx.x;
-  if (co >= p.cout) return;
+  extern __shared__ __align__(16) double fsm[];
+  const int task = blockIdx.x, tid = threadIdx.x, C = p.cout;
+  double* Gs = fsm;                         // [K*K + K]
+  double* ws = Gs + K * K + K;              // [C][K]
+  double* wds = ws + C * K;                 // [C][K]   (DUAL)
+  double* gw = wds + (DUAL ? C * K : 0);    // [C][K]
+  double* gwd = gw + C * K;                 // [C][K]   (DUAL)
   const double* G = p.gram + (long long)task * (K * K + K);
-  const double* sx = G + K * K;
-  const double* A = p.scratch + ((long long)task * p.cout + co) * NA;
-  const float* W = p.w + (long long)task * p.wstride + (long long)co * K;
-  const long long mi = ((long long)task * 2) * p.cout + co;
-  const double mean = (double)p.mean_invstd[mi], r = (double)p.mean_invstd[mi + p.cout];
-  const double gamma = (double)p.gamma[(long long)task * p.gbstride + co];
-  const double s1 = A[K], s2 = A[K + 1], m1 = s1 / p.cnt, m2 = s2 / p.cnt;
-  if (p.bwd_red) { p.bwd_red[mi] = (float)m1; p.bwd_red[mi + p.cout] = (float)m2; }
-  if (p.ssum) {
-    double* dst = p.ssum + ((long long)task * p.cout + co) * NA;
-    for (int i = 0; i < NA; ++i) dst[i] = A[i];
+  for (int i = tid; i < K * K + K; i += blockDim.x) Gs[i] = G[i];
+  const float* W = p.w + (long long)task * p.wstride;
+  const float* Wd = DUAL ? p.wd + (long long)task * p.wdstride : nullptr;
+  for (int i = tid; i < C * K; i += blockDim.x) {
+    ws[i] = (double)W[i];
+    if (DUAL) wds[i] = (double)Wd[i];
   }
-  if (p.out_gamma) {
-    const float bg = p.base_gamma ? p.base_gamma[(long long)task * p.bstride + co] : 0.f;
-    const float bb = p.base_beta ? p.base_beta[(long long)task * p.bstride + co] : 0.f;
-    p.out_gamma[(long long)task * p.ostride + co] = bg + p.scale * (float)s2;
-    p.out_beta[(long long)task * p.ostride + co] = bb + p.scale * (float)s1;
-  }
-  if (p.out_b) p.out_b[(long long)task * p.ostride + co] = p.base_b ? p.base_b[(long long)task * p.bstride + co] : 0.f;
-  if (!p.out_w) return;
-  double wk[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) wk[k] = (double)W[k];
-  for (int k = 0; k < K; ++k) {
-    double gw = 0.0;
-#pragma unroll
-    for (int k2 = 0; k2 < K; ++k2) gw = fma(G[k * K + k2], wk[k2], gw);
-    const double xh = r * (gw - mean * sx[k]);
-    const double dw = gamma * r * (A[k] - m1 * sx[k] - m2 * xh);
-    const float base = p.base_w ? p.base_w[(long long)task * p.bstride + (long long)co * K + k] : 0.f;
-    p.out_w[(long long)task * p.ostride + (long long)co * K + k] = base + p.scale * (float)dw;
-  }
-}
-
-template <int CIN>
-__global__ void img_dual_bwd_finalize_kernel(const ImgK p) {
-  constexpr int K = 9 * CIN, NA = K + 3;
-  const int task = blockIdx.x, co = threadIdx.x;
-  if (co >= p.cout) return;
-  const double* G = p.gram + (long long)task * (K * K + K);
-  const double* sx = G + K * K;
-  const double* A = p.scratch + ((long long)task * p.cout + co) * NA;       // Sd, E1, E2, E3
-  const double* S = p.ssum + ((long long)task * p.cout + co) * NA;          // S, s1, s2 of the primal backward
-  const float* W = p.w + (long long)task * p.wstride + (long long)co * K;
-  const float* Wd = p.wd + (long long)task * p.wdstride + (long long)co * K;
-  const long long mi = ((long long)task * 2) * p.cout + co;
-  const double mean = (double)p.mean_invstd[mi], r = (double)p.mean_invstd[mi + p.cout];
-  const double gamma = (double)p.gamma[(long long)task * p.gbstride + co];
-  const double gdot = (double)p.gammad[(long long)task * p.gbdstride + co];
-  const double m1 = (double)p.bwd_red[mi], m2 = (double)p.bwd_red[mi + p.cout];
-  const double d1 = (double)p.dual_red[mi], d2 = (double)p.dual_red[mi + p.cout];
-  const double e1 = A[K] / p.cnt, e2 = A[K + 1] / p.cnt, e3 = A[K + 2] / p.cnt;
-  const double q = r * (e3 - d1 * m1 - d2 * m2);          // <g * xhat_dot>
-  const double m2dot = e2 + q;
-  const double rdot = -r * r * d2;
-  const double coef = gdot * r + gamma * rdot, gr = gamma * r;
-  if (p.out_gamma) {
-    const float bg = p.base_gamma ? p.base_gamma[(long long)task * p.bstride + co] : 0.f;
-    const float bb = p.base_beta ? p.base_beta[(long long)task * p.bstride + co] : 0.f;
-    p.out_gamma[(long long)task * p.ostride + co] = bg + p.scale * (float)(m2dot * p.cnt);
-    p.out_beta[(long long)task * p.ostride + co] = bb + p.scale * (float)A[K];
-  }
-  if (p.out_b) p.out_b[(long long)task * p.ostride + co] = p.base_b ? p.base_b[(long long)task * p.bstride + co] : 0.f;
-  if (!p.out_w) return;
-  double wk[K], wdk[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) { wk[k] = (double)W[k]; wdk[k] = (double)Wd[k]; }
-  for (int k = 0; k < K; ++k) {
-    double gw = 0.0, gwd = 0.0;
+  __syncthreads();
+  for (int i = tid; i < C * K; i += blockDim.x) {
+    const int co = i / K, k = i - co * K;
+    double a = 0.0, b = 0.0;
 #pragma unroll
     for (int k2 = 0; k2 < K; ++k2) {
-      const double gv = G[k * K + k2];
-      gw = fma(gv, wk[k2], gw);
-      gwd = fma(gv, wdk[k2], gwd);
+      const double gv = Gs[k * K + k2];
+      a = fma(gv, ws[co * K + k2], a);
+      if (DUAL) b = fma(gv, wds[co * K + k2], b);
     }
-    const double xh = r * (gw - mean * sx[k]);
-    const double xhd = r * (gwd - d1 * sx[k] - d2 * xh);
-    const double dense = S[k] - m1 * sx[k] - m2 * xh;
-    const double dwd = coef * dense + gr * (A[k] - e1 * sx[k] - m2 * xhd - m2dot * xh);
-    const float base = p.base_w ? p.base_w[(long long)task * p.bstride + (long long)co * K + k] : 0.f;
-    p.out_w[(long long)task * p.ostride + (long long)co * K + k] = base + p.scale * (float)dwd;
+    gw[i] = a;
+    if (DUAL) gwd[i] = b;
+  }
+  __syncthreads();
+  const double* sx = Gs + K * K;
+  for (int i = tid; i < C * K; i += blockDim.x) {
+    const int co = i / K, k = i - co * K;
+    const double* A = p.scratch + ((long long)task * C + co) * NA;
+    const long long mi = ((long long)task * 2) * C + co;
+    const double mean = (double)p.mean_invstd[mi], r = (double)p.mean_invstd[mi + C];
+    const double gamma = (double)p.gamma[(long long)task * p.gbstride + co];
+    const double xh = r * (gw[i] - mean * sx[k]);
+    double grad;
+    if (!DUAL) {
+      const double m1 = A[K] / p.cnt, m2 = A[K + 1] / p.cnt;
+      grad = gamma * r * (A[k] - m1 * sx[k] - m2 * xh);
+    } else {
+      const double* S = p.ssum + ((long long)task * C + co) * NA;        // sparse sums of the primal backward
+      const double gdot = (double)p.gammad[(long long)task * p.gbdstride + co];
+      const double m1 = (double)p.bwd_red[mi], m2 = (double)p.bwd_red[mi + C];
+      const double d1 = (double)p.dual_red[mi], d2 = (double)p.dual_red[mi + C];
+      const double e1 = A[K] / p.cnt, e2 = A[K + 1] / p.cnt, e3 = A[K + 2] / p.cnt;
+      const double q = r * (e3 - d1 * m1 - d2 * m2);          // <g * xhat_dot>
+      const double m2dot = e2 + q;
+      const double coef = gdot * r - gamma * r * r * d2, gr = gamma * r;
+      const double xhd = r * (gwd[i] - d1 * sx[k] - d2 * xh);
+      grad = coef * (S[k] - m1 * sx[k] - m2 * xh) + gr * (A[k] - e1 * sx[k] - m2 * xhd - m2dot * xh);
+    }
+    if (p.out_w) {
+      const float base = p.base_w ? p.base_w[(long long)task * p.bstride + i] : 0.f;
+      p.out_w[(long long)task * p.ostride + i] = base + p.scale * (float)grad;
+    }
+  }
+  for (int co = tid; co < C; co += blockDim.x) {
+    const double* A = p.scratch + ((long long)task * C + co) * NA;
+    const long long mi = ((long long)task * 2) * C + co;
+    double ggamma, gbeta = A[K];
+    if (!DUAL) {
+      ggamma = A[K + 1];
+      if (p.bwd_red) { p.bwd_red[mi] = (float)(A[K] / p.cnt); p.bwd_red[mi + C] = (float)(A[K + 1] / p.cnt); }
+      if (p.ssum) {
+        double* dst = p.ssum + ((long long)task * C + co) * NA;
+        for (int i = 0; i < NA; ++i) dst[i] = A[i];
+      }
+    } else {
+      const double r = (double)p.mean_invstd[mi + C];
+      const double m1 = (double)p.bwd_red[mi], m2 = (double)p.bwd_red[mi + C];
+      const double d1 = (double)p.dual_red[mi], d2 = (double)p.dual_red[mi + C];
+      const double q = r * (A[K + 2] / p.cnt - d1 * m1 - d2 * m2);
+      ggamma = A[K + 1] + q * p.cnt;
+    }
+    if (p.out_gamma) {
+      const float bg = p.base_gamma ? p.base_gamma[(long long)task * p.bstride + co] : 0.f;
+      const float bb = p.base_beta ? p.base_beta[(long long)task * p.bstride + co] : 0.f;
+      p.out_gamma[(long long)task * p.ostride + co] = bg + p.scale * (float)ggamma;
+      p.out_beta[(long long)task * p.ostride + co] = bb + p.scale * (float)gbeta;
+    }
+    if (p.out_b) p.out_b[(long long)task * p.ostride + co] = p.base_b ? p.base_b[(long long)task * p.bstride + co] : 0.f;
   }
 }
 
@@ -647,9 +647,11 @@ static int launch_bwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   XM_CUDA(cudaMemsetAsync(a->scratch, 0, (size_t)g.tasks * g.cout * NA * sizeof(double), stream));
   img_bwd_kernel<CIN, DUAL><<<dim3(splits, g.tasks, cotiles), IB_THREADS, smem, stream>>>(k);
   if (int rc = launched(DUAL ? "xm_img_dual_bwd(gather)" : "xm_img_bwd(gather)")) return rc;
-  const int threads = ((g.cout + 31) / 32) * 32;
-  if (DUAL) img_dual_bwd_finalize_kernel<CIN><<<g.tasks, threads, 0, stream>>>(k);
-  else img_bwd_finalize_kernel<CIN><<<g.tasks, threads, 0, stream>>>(k);
+  const size_t fsmem = ((size_t)K * K + K + (size_t)(DUAL ? 4 : 2) * g.cout * K) * sizeof(double);
+  XM_REQUIRE(fsmem <= 200 * 1024, "xm_img_bwd: too many channels for the finalize kernel");
+  static bool fattr = false;
+  if (!fattr) { XM_CUDA(cudaFuncSetAttribute(img_finalize_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); fattr = true; }
+  img_finalize_kernel<CIN, DUAL><<<g.tasks, 256, fsmem, stream>>>(k);
   return launched(DUAL ? "xm_img_dual_bwd(finalize)" : "xm_img_bwd(finalize)");
 }
 

@@ -15,7 +15,7 @@ namespace xm {
 
 extern int g_precise;
 extern int g_use_tc;
-int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out);
+int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ctas_out, int* tiles_out);
 long long wgrad_tc_partial_floats(const XmBlockGeom& g);
 
 constexpr int WG_THREADS = 128;
@@ -323,19 +323,28 @@ static int wgrad_img_splits(const XmBlockGeom& g) {
 
 // out_w[task][co][ci][tap] = base_w + scale * sum_split partial[task][split][tap*cin+ci][co]  (double sum)
 // out_b[task][co] = base_b (the conv-bias gradient is analytically zero under train-mode BN).
+// ctas > 0: the partials come from a persistent grid of `ctas` CTAs over the flattened (task, tile) list
+// (wgrad_tc.cu); task t then owns slots 0 .. last(t) - first(t) of its `splits` slots.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
                                     float* out_w, float* out_b, long long out_stride,
                                     const float* base_w, const float* base_b, long long base_stride,
-                                    float scale) {
+                                    float scale, int ctas = 0, int tiles_per_task = 0) {
   const int task = blockIdx.y;
   const int per = 9 * cin * cout;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int used = splits;
+  if (ctas > 0) {
+    const long long G = (long long)gridDim.y * tiles_per_task;
+    const int first = (int)((((long long)task * tiles_per_task + 1) * ctas + G - 1) / G) - 1;
+    const int last = (int)((((long long)(task + 1) * tiles_per_task) * ctas + G - 1) / G) - 1;
+    used = last - first + 1;
+  }
   if (i < per) {
     const int row = i / cout, co = i - row * cout;
     const int tap = row / cin, ci = row - tap * cin;
     const float* P = partial + (long long)task * splits * per + i;
     double s = 0.0;
-    for (int k = 0; k < splits; ++k) s += (double)P[(long long)k * per];
+    for (int k = 0; k < used; ++k) s += (double)P[(long long)k * per];
     const long long o = ((long long)co * cin + ci) * 9 + tap;
     const float b = base_w ? base_w[(long long)task * base_stride + o] : 0.f;
     out_w[(long long)task * out_stride + o] = b + scale * (float)s;
@@ -389,15 +398,15 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
   if (g_use_tc && g_precise) {
     // 32-channel stride-1 layers run on the tcgen05 / TMEM kernel (wgrad_tc.cu)
     XM_REQUIRE(a->partial_bytes >= wgrad_tc_partial_floats(g) * 4, "xm_wgrad: partial buffer too small");
-    int rc = 0;
-    const int tsplits = wgrad_tc_try(a, stream, &rc);
+    int rc = 0, tc_ctas = 0, tc_tiles = 0;
+    const int tsplits = wgrad_tc_try(a, stream, &rc, &tc_ctas, &tc_tiles);
     if (tsplits < 0) return rc;
     if (tsplits > 0) {
       const int per = 9 * g.cin * g.cout;
       dim3 rgrid((per + 255) / 256, g.tasks);
       wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, tsplits, g.cin, g.cout, a->out_w, a->out_b,
                                                     a->out_task_stride, a->base_w, a->base_b,
-                                                    a->base_task_stride, a->scale);
+                                                    a->base_task_stride, a->scale, tc_ctas, tc_tiles);
       return launched("xm_wgrad(reduce)");
     }
   }

@@ -33,7 +33,7 @@ constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 96, 1, 1);   // A and B MN-ma
 struct WgradTcK {
   int tasks, n, H, W, Hp, Wp, Q;
   PosMap pm;
-  int tiles_per_task, splits, npairs;
+  int tiles_per_task, splits, npairs, ctas;
   int Rx, Rg, xbuf, gbuf;             // staged x / g rows per tile, bytes of one x / g buffer (hi or lo)
   int off_x0, off_x1, off_g0, off_g1, off_bar;   // shared-memory byte offsets
   const float* x[2];
@@ -44,7 +44,6 @@ struct WgradTcK {
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int task = blockIdx.y, split = blockIdx.x;
   const int xset = p.xbuf, gset = p.gbuf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -80,7 +79,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ntiles = (p.tiles_per_task - split + p.splits - 1) / p.splits;
+  // persistent CTA over the flattened (task, tile) list: CTA c owns tiles [c*G/n, (c+1)*G/n) -- every SM gets the
+  // same share whatever the task count.  The pipeline streams straight through task boundaries; only the drain
+  // flushes its register accumulators when the task changes.  Partial slot of (CTA c, task t) = c - first CTA of t.
+  const long long G = (long long)p.tasks * p.tiles_per_task;
+  const int g_lo = (int)(G * blockIdx.x / gridDim.x), g_hi = (int)(G * (blockIdx.x + 1) / gridDim.x);
+  const int ntiles = g_hi - g_lo;
   const int nunits = ntiles * p.npairs;
 
   if (warp < 4) {
@@ -93,8 +97,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int c = 0; c < 32; ++c) macc[a][c] = 0.f;
+      auto flush = [&](int task) {
+        const int first = (int)((((long long)task * p.tiles_per_task + 1) * gridDim.x + G - 1) / G) - 1;   // first CTA of the task
+        float* P = p.partial + ((long long)task * p.splits + ((int)blockIdx.x - first)) * 9 * 32 * 32;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float4* dst = reinterpret_cast<float4*>(P + (((2 - j) * 3 + warp) * 32 + lane) * 32);   // tap (kh = 2-j, kw)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            dst[c] = make_float4(macc[j][4 * c], macc[j][4 * c + 1], macc[j][4 * c + 2], macc[j][4 * c + 3]);
+            macc[j][4 * c] = macc[j][4 * c + 1] = macc[j][4 * c + 2] = macc[j][4 * c + 3] = 0.f;
+          }
+        }
+      };
+      int cur_task = g_lo / p.tiles_per_task;
       for (int it = 0; it < ntiles; ++it) {
         const int set = it & 1;
+        const int t_task = (g_lo + it) / p.tiles_per_task;
+        if (t_task != cur_task) { flush(cur_task); cur_task = t_task; }
         mbar_wait(bar_tfull + 8 * set, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(set * 96);
@@ -108,14 +128,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         tc_fence_before();
         mbar_arrive(bar_tfree + 8 * set);
       }
-      float* P = p.partial + ((long long)task * p.splits + split) * 9 * 32 * 32;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float4* dst = reinterpret_cast<float4*>(P + (((2 - j) * 3 + warp) * 32 + lane) * 32);   // tap (kh = 2-j, kw)
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          dst[c] = make_float4(macc[j][4 * c], macc[j][4 * c + 1], macc[j][4 * c + 2], macc[j][4 * c + 3]);
-      }
+      if (ntiles > 0) flush(cur_task);
     }
   } else if (warp < 11) {
     // ========================================= producers =============================================
@@ -130,7 +143,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     struct Regs { float4 x[6]; float4 g[8]; };
     auto issue = [&](int u, Regs& r) {
       const int it = u / p.npairs, pair = u - it * p.npairs;
-      const int q0 = (split + it * p.splits) * 128;
+      const int gtile = g_lo + it, task = gtile / p.tiles_per_task;
+      const int q0 = (gtile - task * p.tiles_per_task) * 128;
       const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
       const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
 #pragma unroll
@@ -251,10 +265,10 @@ static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
   p.off_g1 = p.off_x1 + 2 * p.xbuf;
   p.off_bar = p.off_g1 + 2 * p.gbuf;
   smem = (size_t)p.off_bar + 8 * 8 + 16;
-  int splits = num_sms() / g.tasks;
-  if (splits < 1) splits = 1;
-  if (splits > p.tiles_per_task) splits = p.tiles_per_task;
-  p.splits = splits;
+  // partial slots per task = the most CTAs of the persistent grid that can touch one task
+  const long long total = (long long)g.tasks * p.tiles_per_task;
+  p.ctas = (int)(total < num_sms() ? total : num_sms());
+  p.splits = (p.ctas + g.tasks - 1) / g.tasks + 1;
   return smem <= 227 * 1024 && p.Rg <= WT_PRODUCERS;     // a producer thread stages <= 4 g rows per unit
 }
 
@@ -266,8 +280,10 @@ long long wgrad_tc_partial_floats(const XmBlockGeom& g) {
   return (long long)g.tasks * p.splits * 9 * 32 * 32;
 }
 
-// Returns the number of splits written to a->partial (>0) when handled, 0 when not covered, <0 on error.
-int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out) {
+// Returns the number of partial slots per task in a->partial (>0) when handled (slot j of task t is written by CTA
+// first(t) + j of the persistent grid; wgrad_reduce_kernel derives each task's slot count from *ctas_out and
+// *tiles_out), 0 when not covered, <0 on error.
+int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ctas_out, int* tiles_out) {
   const XmBlockGeom& g = a->g;
   *rc_out = 0;
   if (a->src_nchw) return 0;
@@ -284,9 +300,10 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out) {
     if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
   }
-  dim3 grid(p.splits, g.tasks);
-  wgrad_tc_kernel<<<grid, WT_THREADS, smem, stream>>>(p);
+  wgrad_tc_kernel<<<p.ctas, WT_THREADS, smem, stream>>>(p);
   if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
+  *ctas_out = p.ctas;
+  *tiles_out = p.tiles_per_task;
   return p.splits;
 }
 
