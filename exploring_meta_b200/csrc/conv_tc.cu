@@ -34,8 +34,10 @@
 namespace xm {
 
 constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs  (12 warps = 3 per scheduler: 168 registers each)
-constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11 [, 12-15])
-constexpr int TC_GROUPS = 1;          // drain groups: group g drains tiles g, g + TC_GROUPS, ... (TMEM set = tile & 1)
+constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11, 12-15)
+constexpr int TC_GROUPS = 2;          // drain groups: group g drains tiles g, g + 2, ... (= TMEM set g): a tile's drain is
+                                      // latency-bound (TMEM loads, shuffles, exchange) and ~1.5x the MMA time of a tile,
+                                      // so two tiles are drained concurrently (16 warps: 128 registers each)
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
 constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows minus the two shifted-out rows
 constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   unsigned char* Abase = smem + 2 * BFLOATS * 4;               // stage s: hi at s*2*set, lo at (s*2+1)*set
   uint64_t* bars = reinterpret_cast<uint64_t*>(Abase + 4 * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* xch = reinterpret_cast<float*>(bars + 10);            // [4 buffers][4 warps][3][16] boundary rows
+  float* xch = reinterpret_cast<float*>(bars + 10);            // [tile & 3][half][4 warps][3][16] boundary rows
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
                  bar_tfree = smem_u32(bars + 6);
 
@@ -199,9 +201,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     const int quarter = warp & 3;                              // TMEM lane quarter of this warp (= warp id % 4)
     const int group = (warp - 8) >> 2;
     const int row = quarter * 32 + lane;
-    float ssum[32], ssq[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) ssum[c] = ssq[c] = 0.f;
+    // BatchNorm statistics: after each tile the warp's 32 rows are summed with a shuffle reduce-scatter, which leaves
+    // lane l with channel l's partial (2 doubles of state instead of 64 per-thread fp32 accumulators -- this is what
+    // lets 16 warps fit the register file)
+    double dsum = 0.0, dsq = 0.0;
 #ifdef XM_TC_TIMING
     long long t_wait = 0, t_tmem = 0, t_rest = 0, t0;
 #endif
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       // ---- TMEM phase: both 16-column halves -> registers (kw shifts applied), then the set is released --------
       auto load_half = [&](int half, float (&acc)[16]) {
         // one 16-column block at a time (register pressure): kw = 1, kw = 2, then the thread's own kw = 0 block
-        float* xb = xch + ((((it & 1) * 2 + half) * 4 + quarter) * 3) * 16;
+        float* xb = xch + ((((it & 3) * 2 + half) * 4 + quarter) * 3) * 16;
 #pragma unroll
         for (int blk = 1; blk <= 3; ++blk) {
           const int kw = blk % 3;                                  // 1, 2, 0
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         for (int half = 0; half < 2; ++half) {
           // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
           // (16-byte loads, all issued before the first use: one shared-memory round trip instead of 48)
-          const float4* xn = reinterpret_cast<const float4*>(xch + ((((it & 1) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
+          const float4* xn = reinterpret_cast<const float4*>(xch + ((((it & 3) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
           float4 a[4], b[4];
           const int oa = lane == 31 ? 0 : 4;                     // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
 #pragma unroll
@@ -298,25 +301,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float (&acc)[16] = acc2[half];
-        if (valid) {
-          if (p.stat_mode == XM_STAT_SUM_SQ) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              ssum[half * 16 + k] += acc[k];
-              ssq[half * 16 + k] = fmaf(acc[k], acc[k], ssq[half * 16 + k]);
-            }
-          } else if (p.stat_mode == XM_STAT_SUM_AUX) {
-            const float4* ax = reinterpret_cast<const float4*>(p.aux + o + half * 16);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 a4 = __ldg(ax + k);
-              const int b = half * 16 + 4 * k;
-              ssum[b] += acc[4 * k]; ssum[b + 1] += acc[4 * k + 1]; ssum[b + 2] += acc[4 * k + 2]; ssum[b + 3] += acc[4 * k + 3];
-              ssq[b] = fmaf(acc[4 * k], a4.x, ssq[b]); ssq[b + 1] = fmaf(acc[4 * k + 1], a4.y, ssq[b + 1]);
-              ssq[b + 2] = fmaf(acc[4 * k + 2], a4.z, ssq[b + 2]); ssq[b + 3] = fmaf(acc[4 * k + 3], a4.w, ssq[b + 3]);
-            }
-          }
-        }
         // Store with full 32-byte sectors: lanes (2i, 2i+1) swap half of their float4s so that in every store
         // instruction the pair writes 32 contiguous bytes of ONE row (a thread's own row is 4 float4 = 64 B of
         // this half; 16-byte pieces of 32 different rows per instruction would be partial-sector writes).
@@ -349,6 +333,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           }
         }
       }
+      if (p.stat_mode) {
+        // v1 = this row's 32 outputs (0 for rows that produce none), v2 = v1^2 or v1 * aux
+        float v1[32], v2[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v1[k] = valid ? acc2[k >> 4][k & 15] : 0.f;
+        if (p.stat_mode == XM_STAT_SUM_SQ) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v2[k] = v1[k] * v1[k];
+        } else {
+          const float4* ax = reinterpret_cast<const float4*>(p.aux + o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 a4 = __ldg(ax + k);
+            v2[4 * k] = v1[4 * k] * a4.x; v2[4 * k + 1] = v1[4 * k + 1] * a4.y;
+            v2[4 * k + 2] = v1[4 * k + 2] * a4.z; v2[4 * k + 3] = v1[4 * k + 3] * a4.w;
+          }
+        }
+        // reduce-scatter over the 32 lanes: at offset `off` a lane keeps the half of its values whose channel bit
+        // `off` equals its own lane bit and receives the partner's copy of that half (31 shuffles per array)
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float s1 = __shfl_xor_sync(0xffffffffu, up ? v1[i] : v1[i + off], off);
+            const float s2 = __shfl_xor_sync(0xffffffffu, up ? v2[i] : v2[i + off], off);
+            v1[i] = (up ? v1[i + off] : v1[i]) + s1;
+            v2[i] = (up ? v2[i + off] : v2[i]) + s2;
+          }
+        }
+        dsum += (double)v1[0];
+        dsq += (double)v2[0];
+      }
     }
 #ifdef XM_TC_TIMING
     t_rest = clock64() - t0;
@@ -357,16 +374,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
              t_wait / ntiles, t_tmem / ntiles, t_rest);
 #endif
     if (p.stat_mode) {
-      // per-thread fp32 partials (<= a few hundred terms each) -> double across the warp -> global atomics
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const double a = warp_sum((double)ssum[c]);
-        const double b = warp_sum((double)ssq[c]);
-        if (lane == 0) {
-          atomicAdd(&p.stats[((long long)task * 2) * 32 + c], a);
-          atomicAdd(&p.stats[((long long)task * 2 + 1) * 32 + c], b);
-        }
-      }
+      // lane l holds channel l's sums over this warp's rows of all its tiles
+      atomicAdd(&p.stats[((long long)task * 2) * 32 + lane], dsum);
+      atomicAdd(&p.stats[((long long)task * 2 + 1) * 32 + lane], dsq);
     }
   } else {
     // ======================================= MMA issuer =================================================
@@ -443,7 +453,7 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
   R = 128 + 2 * Wp;
   const int rpad = R | 1;                 // odd row count per plane: conflict-free 16 B stores across planes
   plane_bytes = rpad * 16;
-  return (size_t)2 * (3 * 8 * 96 * 4) * 4 + (size_t)4 * 8 * plane_bytes + 10 * 8 + 4 * 4 * 3 * 16 * 4;
+  return (size_t)2 * (3 * 8 * 96 * 4) * 4 + (size_t)4 * 8 * plane_bytes + 10 * 8 + 8 * 4 * 3 * 16 * 4;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
