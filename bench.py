@@ -381,7 +381,7 @@ def run_ours(args):
             elif 'tflops' in fam:
                 fam['roofline_frac'] = round(fam['tflops'] / peaks['tensor_tflops'], 4)
         traffic = {}
-        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')     # written by scripts/ncu_digest.py
         if os.path.isfile(tpath):
             with open(tpath) as f:
                 traffic = json.load(f)
@@ -400,8 +400,8 @@ def run_ours(args):
             line['roofline'] = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_tflops'],
                                 'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': tr,
                                 'peak_source': peaks['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json); the '
-                                'kernel computes fp32-grade products as 3 TF32 tcgen05.mma each with N = 32 tiles, so '
-                                'its own ceiling is ~7% of this peak (DESIGN.md section 4)',
+                                'kernel computes fp32-grade products as 3 TF32 tcgen05.mma each (TF32 dense = 1/2 of the bf16 '
+                                'rate), so its own ceiling is 1/6 of this peak (DESIGN.md section 4)',
                                 'algorithmic_flops_per_launch': w['flops'] / tv['calls'],
                                 'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
     if world == 1 and not args.no_cpu_baseline:

@@ -25,7 +25,13 @@ cols = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'time_us'), ('dram
 cols = [(c, n) for c, n in cols if c in idx]
 # the entry-point call each kernel belongs to: profile_calls.py prints them in launch order; a call may launch
 # several kernels, so kernels are matched to calls by name below
-calls = [l.split('profiled: ')[1].strip() for l in open(log) if l.startswith('profiled: ')]
+calls = []
+for l in open(log):
+    if l.startswith('profiled: '):
+        parts = [x.strip() for x in l.split('profiled: ')[1].split('|')]
+        nk = int(parts[1].split()[1]) if len(parts) > 1 else None
+        cps = int(parts[2].split()[1]) if len(parts) > 2 else 0
+        calls.append((parts[0], nk, cps))
 
 
 def to_mb(v, unit):
@@ -47,3 +53,31 @@ with open(out + '.csv', 'w', newline='') as f:
             line.append(v)
         w.writerow(line)
 print('wrote', out + '.csv', len(rows) - 2, 'kernels;', len(calls), 'calls profiled')
+
+# ---- DRAM traffic per entry-point call, averaged per family over the calls of one config-2 step -------------
+if calls and all(nk is not None for _k, nk, _c in calls) and sum(nk for _k, nk, _c in calls) == len(rows) - 2:
+    def family(key):
+        name = key.split()[0]
+        if name in ('xm_conv', 'xm_wgrad') and ' cin3 ' in key + ' ':
+            return name + ':image_layer'
+        return name
+    fams, r = {}, 2
+    for key, nk, cps in calls:
+        dram = 0.0
+        names = []
+        for rr in rows[r:r + nk]:
+            dram += to_mb(rr[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) * 1e6
+            dram += to_mb(rr[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']]) * 1e6
+            names.append(re.sub(r'\(.*', '', rr[idx['Kernel Name']].replace('void ', '')))
+        r += nk
+        f = fams.setdefault(family(key), {'bytes': 0.0, 'calls': 0, 'per_call': {}})
+        f['bytes'] += dram * cps
+        f['calls'] += cps
+        f['per_call'][key] = {'dram_bytes': dram, 'calls_per_step': cps, 'kernels': names}
+    traffic = {k: {'dram_bytes_per_launch': v['bytes'] / max(v['calls'], 1), 'calls_per_step': v['calls'],
+                   'per_call': v['per_call']} for k, v in fams.items()}
+    with open(out + '_traffic.json', 'w') as f:
+        json.dump(traffic, f, indent=1)
+    print('wrote', out + '_traffic.json')
+else:
+    print('no per-call kernel counts in the log: traffic json not written')

@@ -52,10 +52,21 @@ for fn, args, name in e.prog.calls:
         continue
     seen.add(k)
     chosen.append((fn, args, k))
+# how often each distinct call occurs in the full config-2 program (5 inner steps): weights for per-family averages
+e5 = eng.MamlEngine(spec, a.tasks, 5, 5, 0.5, device='cuda')
+count5 = {}
+for _fn, args, name in e5.prog.calls:
+    if not isinstance(args, tuple):
+        count5[key(name, args)] = count5.get(key(name, args), 0) + 1
+del e5
+lib = _lib.load()
+kernels = []
 torch.cuda.profiler.start()
 for fn, args, k in chosen:
+    n0 = lib.xm_launch_count()
     _lib.check(fn(ctypes.byref(args), stream), k)
+    kernels.append(lib.xm_launch_count() - n0)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-for _fn, _a, k in chosen:
-    print('profiled:', k)
+for (_fn, _a, k), n in zip(chosen, kernels):
+    print('profiled: %s | kernels %d | calls_per_step %d' % (k, n, count5.get(k, 0)))
