@@ -372,35 +372,46 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_fwd_kernel(const ImgK p) {
 template <int CIN, int DUAL>
 __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
   constexpr int K = 9 * CIN, NA = K + 3;
-  extern __shared__ __align__(16) float4 sm4[];
+  extern __shared__ __align__(16) float bsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int task = blockIdx.y, split = blockIdx.x, co0 = blockIdx.z * 32;
-  const int Wp = p.W + 2;
-  const int band_px = (2 * IB_PROWS + 2) * Wp + 8;
-  float4* band = sm4;                                                     // 2 x band_px
-  double* red = reinterpret_cast<double*>(band + 2 * band_px);            // [warps][NA][32]: a thread owns its slots
-  for (int i = tid; i < 2 * band_px; i += IB_THREADS) band[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int Wp = p.W + 2, rows = 2 * IB_PROWS + 2;
+  const int plane = rows * Wp, band_fl = CIN * plane + 8;
+  // The image band is staged PLANAR ([cin][row][col] floats): the 32 lanes of a patch load then touch at most four
+  // addresses (the four window positions) in four different banks -- one shared-memory wavefront per LDS.32, 27 per
+  // pooled pixel, where 16-byte pixel vectors cost 36 (a 128-bit load is served a quarter warp at a time).
+  float* band = bsm;                                                       // 2 x band_fl
+  double* red = reinterpret_cast<double*>(bsm + ((2 * band_fl + 1) & ~1)); // [warps][NA][32]: a thread owns its slots
+  for (int i = tid; i < 2 * band_fl; i += IB_THREADS) band[i] = 0.f;
   for (int i = tid; i < (IB_THREADS / 32) * NA * 32; i += IB_THREADS) red[i] = 0.0;
   double* const mine = red + (warp * NA) * 32 + lane;
   __syncthreads();
   const int bands_per_img = (p.hp + IB_PROWS - 1) / IB_PROWS, nbands = p.n * bands_per_img;
-  if (split < nbands) {
-    const int img = split / bands_per_img, py0 = (split - img * bands_per_img) * IB_PROWS;
-    issue_band<CIN>(p, image_ptr(p, task, img, CIN), 2 * py0 - 1, 2 * IB_PROWS + 2, band);
-  }
+  const int chw = p.H * p.W;
+  auto issue = [&](int b, float* dst) {
+    const int img = b / bands_per_img, py0 = (b - img * bands_per_img) * IB_PROWS;
+    const float* X = image_ptr(p, task, img, CIN);
+    for (int i = tid; i < CIN * plane; i += IB_THREADS) {
+      const int c = i / plane, r = i - c * plane;
+      const int yy = r / Wp, xx = r - yy * Wp, y = 2 * py0 - 1 + yy, x = xx - 1;
+      const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
+      cp_async4(dst + i, in ? X + (long long)c * chw + y * p.W + x : X, in ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+  if (split < nbands) issue(split, band);
   const long long mi = ((long long)task * 2) * p.cout + co0 + lane;
   const float mean = __ldg(p.mean_invstd + mi), rinv = __ldg(p.mean_invstd + mi + p.cout);
-  float facc[NA];                 // fp32 over one band (~16 winners per thread), flushed into the double slots
+  float facc[NA];                 // fp32 over four bands (~64 winners per thread), then into the thread's double slots
 #pragma unroll
   for (int i = 0; i < NA; ++i) facc[i] = 0.f;
 
-  int kbuf = 0;
+  int kbuf = 0, nb_done = 0;
   for (int b = split; b < nbands; b += p.splits, kbuf ^= 1) {
     const int img = b / bands_per_img, py0 = (b - img * bands_per_img) * IB_PROWS;
-    const float4* const cur = band + kbuf * band_px;
+    const float* const cur = band + kbuf * band_fl;
     if (b + p.splits < nbands) {
-      const int nb = b + p.splits, nimg = nb / bands_per_img, npy0 = (nb - nimg * bands_per_img) * IB_PROWS;
-      issue_band<CIN>(p, image_ptr(p, task, nimg, CIN), 2 * npy0 - 1, 2 * IB_PROWS + 2, band + (kbuf ^ 1) * band_px);
+      issue(b + p.splits, band + (kbuf ^ 1) * band_fl);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -435,22 +446,25 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
         facc[K] += c;
         facc[K + 1] = fmaf(c, xhat, facc[K + 1]);
         if (DUAL) facc[K + 2] = fmaf(gg, zd[e], facc[K + 2]);
-        const float4* src = cur + (2 * pyl + dy) * Wp + 2 * px + dx;
+        const float* src = cur + (2 * pyl + dy) * Wp + 2 * px + dx;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+        for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float4 v = src[kh * Wp + kw];
-            const float vv[4] = {v.x, v.y, v.z, v.w};
+          for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) facc[ci * 9 + kh * 3 + kw] = fmaf(c, vv[ci], facc[ci * 9 + kh * 3 + kw]);
-          }
+            for (int kw = 0; kw < 3; ++kw)
+              facc[ci * 9 + kh * 3 + kw] = fmaf(c, src[ci * plane + kh * Wp + kw], facc[ci * 9 + kh * 3 + kw]);
       }
     }
+    if ((++nb_done & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) { mine[i * 32] += (double)facc[i]; facc[i] = 0.f; }
+      for (int i = 0; i < NA; ++i) { mine[i * 32] += (double)facc[i]; facc[i] = 0.f; }
+    }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) mine[i * 32] += (double)facc[i];
+  __syncthreads();
   double* out = p.scratch + ((long long)task * p.cout + co0) * NA;
   for (int i = tid; i < NA * 32; i += IB_THREADS) {
     const int co = i / NA, q = i - co * NA;
@@ -635,7 +649,8 @@ template <int CIN, int DUAL>
 static int launch_bwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   constexpr int K = 9 * CIN, NA = K + 3;
   const XmBlockGeom& g = a->g;
-  const size_t smem = 2 * ((size_t)(2 * IB_PROWS + 2) * (g.win + 2) + 8) * 16 + (size_t)(IB_THREADS / 32) * NA * 32 * 8;
+  const size_t band_fl = (size_t)CIN * (2 * IB_PROWS + 2) * (g.win + 2) + 8;
+  const size_t smem = ((2 * band_fl + 1) & ~(size_t)1) * 4 + (size_t)(IB_THREADS / 32) * NA * 32 * 8;
   XM_REQUIRE(smem <= 200 * 1024, "xm_img_bwd: image too wide");
   static bool attr = false;
   if (!attr) { XM_CUDA(cudaFuncSetAttribute(img_bwd_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
