@@ -1,0 +1,110 @@
+"""BASELINE.json's full size (config 2: 32 tasks x 50 images of 84x84x3, 5 inner steps) is far beyond what the CPU
+oracle finishes in seconds, so parity at that size is checked through size-independent properties of the domain:
+
+* task independence: tasks only interact through the sum of their meta-gradients (vision/maml_vision.py:102-112), so
+  a 32-task launch program must give every task the result a 4-task program gives it;
+* the meta-gradient is the gradient of what `fast_adapt` returns: its inner product with a direction equals the
+  central difference of the mean adapted query loss along that direction (adaptation included -- this exercises
+  the second-order term without an oracle);
+* the summed gradient equals the task-ordered sum of the per-task outer cotangents, first-order mode differs from
+  second-order mode, and the headline configuration (inner lr 0.5) runs to finite numbers.
+The small-size twins of these launch programs are compared with the oracle in test_gpu_parity.py / test_gpu_golden.py.
+"""
+import pytest
+import torch
+
+from exploring_meta_b200 import engine as eng
+from exploring_meta_b200 import spec as pspec
+from exploring_meta_b200.synthetic import make_tasks
+
+pytestmark = pytest.mark.gpu
+
+TASKS, WAYS, SHOTS, STEPS = 32, 5, 5, 5
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def setup():
+    spec = pspec.miniimagenet_spec(WAYS)
+    theta = pspec.init_flat_params(spec, seed=42).cuda()
+    X, Y = make_tasks(TASKS, WAYS, SHOTS, (3, 84, 84), seed=0)
+    return spec, theta, X.cuda(), Y.cuda()
+
+
+def test_config2_task_independence(setup):
+    spec, theta, X, Y = setup
+    lr = 0.001                                    # calm inner lr: fp32 reassociation noise is not amplified
+    big = eng.MamlEngine(spec, TASKS, SHOTS, STEPS, lr, device='cuda')
+    big.run(X, Y, theta)
+    torch.cuda.synchronize()
+    loss, correct = big.loss.clone(), big.correct.clone()
+    theta_T = big.theta_steps[STEPS - 1].clone()
+    assert big.img, 'config 2 must take the fused image-block path'
+    bar_sum = big.grad.clone()
+    del big
+    small = eng.MamlEngine(spec, 4, SHOTS, STEPS, lr, device='cuda')
+    gsum = torch.zeros_like(bar_sum)
+    for t0 in range(0, TASKS, 4):
+        small.run(X[t0:t0 + 4], Y[t0:t0 + 4], theta)
+        torch.cuda.synchronize()
+        assert torch.allclose(small.loss, loss[t0:t0 + 4], rtol=2e-5, atol=1e-6)
+        assert small.correct.tolist() == correct[t0:t0 + 4].tolist()
+        for t in range(4):
+            assert _rel(small.theta_steps[STEPS - 1, t], theta_T[t0 + t]) < 1e-5
+        gsum += small.grad
+    # the 32-task meta-gradient is the sum of the eight 4-task ones
+    assert _rel(gsum, bar_sum) < 1e-4
+
+
+def test_config2_meta_gradient_is_the_gradient_of_the_adapted_loss(setup):
+    spec, theta, X, Y = setup
+    lr, steps = 0.05, 2                            # adaptation moves the weights, smooth enough for central differences
+    e = eng.MamlEngine(spec, TASKS, SHOTS, steps, lr, device='cuda')
+    e.run(X, Y, theta)
+    torch.cuda.synchronize()
+    g = e.grad.clone() / TASKS                     # gradient of the MEAN query loss
+    fo = eng.MamlEngine(spec, TASKS, SHOTS, steps, lr, mode='first', device='cuda')
+    fo.run(X, Y, theta)
+    torch.cuda.synchronize()
+    g1 = fo.grad.clone() / TASKS
+    del e, fo
+    ev = eng.MamlEngine(spec, TASKS, SHOTS, steps, lr, mode='eval', device='cuda')
+
+    def mean_loss(th):
+        ev.run(X, Y, th)
+        torch.cuda.synchronize()
+        return ev.loss.double().mean().item()
+
+    # the Hessian term is part of what is being checked: first- and second-order gradients must differ measurably
+    assert _rel(g1, g) > 1e-4
+    torch.manual_seed(0)
+    for trial in range(3):
+        v = g / g.norm() if trial == 0 else torch.randn_like(g)
+        v = v / v.norm()
+        h = 2e-3
+        fd = (mean_loss(theta + h * v) - mean_loss(theta - h * v)) / (2 * h)
+        an = torch.dot(g.double(), v.double()).item()
+        scale = max(abs(an), 0.05 * g.norm().item())
+        assert abs(fd - an) <= 0.05 * scale, 'trial %d: central difference %.6f vs <grad, v> %.6f' % (trial, fd, an)
+
+
+def test_config2_headline_runs_finite(setup):
+    spec, theta, X, Y = setup
+    e = eng.MamlEngine(spec, TASKS, SHOTS, STEPS, 0.5, device='cuda')
+    e.capture()
+    e.run(X, Y, theta)
+    torch.cuda.synchronize()
+    g_a, loss_a = e.grad.clone(), e.loss.clone()
+    assert torch.isfinite(g_a).all() and torch.isfinite(loss_a).all()
+    assert int(e.correct.min()) >= 0 and int(e.correct.max()) <= WAYS * SHOTS
+    # conv biases are cancelled by train-mode BatchNorm: their meta-gradient is exactly zero
+    offs, _ = spec.param_offsets()
+    for l in range(spec.layers):
+        o = offs[4 * l + 3]
+        assert float(g_a[o:o + spec.hidden].abs().max()) <= 1e-5 * float(g_a.abs().max())
+    e.run(X, Y, theta)                               # graph replay on the same inputs: same counts of finite outputs
+    torch.cuda.synchronize()                         # (inner lr 0.5 amplifies reduction-order noise: no bitwise claim)
+    assert torch.isfinite(e.grad).all() and torch.isfinite(e.loss).all()
