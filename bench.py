@@ -246,6 +246,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     lib.xm_set_precision(0 if args.fast_tf32 else 1)

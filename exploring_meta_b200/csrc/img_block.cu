@@ -391,11 +391,16 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
   auto issue = [&](int b, float* dst) {
     const int img = b / bands_per_img, py0 = (b - img * bands_per_img) * IB_PROWS;
     const float* X = image_ptr(p, task, img, CIN);
-    for (int i = tid; i < CIN * plane; i += IB_THREADS) {
-      const int c = i / plane, r = i - c * plane;
-      const int yy = r / Wp, xx = r - yy * Wp, y = 2 * py0 - 1 + yy, x = xx - 1;
-      const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
-      cp_async4(dst + i, in ? X + (long long)c * chw + y * p.W + x : X, in ? 4 : 0);
+    // one (channel, band row) per warp step, lanes over the columns: no per-element index arithmetic
+    for (int cr = warp; cr < CIN * rows; cr += IB_THREADS / 32) {
+      const int c = cr / rows, yy = cr - c * rows, y = 2 * py0 - 1 + yy;
+      const bool rowin = y >= 0 && y < p.H;
+      const float* src = X + (long long)c * chw + (rowin ? y : 0) * p.W - 1;
+      float* d = dst + cr * Wp;
+      for (int xx = lane; xx < Wp; xx += 32) {
+        const bool in = rowin && xx >= 1 && xx <= p.W;
+        cp_async4(d + xx, in ? src + xx : X, in ? 4 : 0);
+      }
     }
     cp_async_commit();
   };
@@ -419,16 +424,25 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
     __syncthreads();
     const int prows = min(IB_PROWS, p.hp - py0), npx = prows * p.wp;
     const long long obase = ((((long long)task * p.n + img) * p.hp + py0) * p.wp) * p.cout + co0 + lane;
+    // pooled pixel j <-> (row jy[e], column jx[e]) of the band, advanced incrementally (16 pixels per step)
+    int jy[2], jx[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = warp + e * (IB_THREADS / 32);
+      jy[e] = j / p.wp;
+      jx[e] = j - jy[e] * p.wp;
+    }
     for (int j0 = warp; j0 < npx; j0 += 2 * (IB_THREADS / 32)) {
       float g[2], gd[2], zs[2], zd[2];
       unsigned s[2];
-      int jj[2];
+      bool live[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = j0 + e * (IB_THREADS / 32);
-        jj[e] = j < npx ? j : -1;
-        const long long o = obase + (long long)(j < npx ? j : j0) * p.cout;
-        g[e] = __ldg(p.gp + o);
+        live[e] = j < npx;
+        const float* q = p.gp + obase + (long long)(live[e] ? j : j0) * p.cout;
+        const long long o = q - p.gp;
+        g[e] = __ldg(q);
         zs[e] = __ldg(p.zsel + o);
         s[e] = __ldg(p.sel + o);
         if (DUAL) { gd[e] = p.gpd ? __ldg(p.gpd + o) : 0.f; zd[e] = __ldg(p.zdsel + o); }
@@ -436,9 +450,8 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
       }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const bool on = jj[e] >= 0 && s[e] != 255u;
-        const int j = jj[e] >= 0 ? jj[e] : 0;
-        const int pyl = j / p.wp, px = j - pyl * p.wp;
+        const bool on = live[e] && s[e] != 255u;
+        const int pyl = live[e] ? jy[e] : 0, px = live[e] ? jx[e] : 0;
         const int dy = on ? (int)(s[e] >> 1) : 0, dx = on ? (int)(s[e] & 1u) : 0;
         const float gg = on ? g[e] : 0.f, ggd = on ? gd[e] : 0.f;
         const float xhat = (zs[e] - mean) * rinv;
@@ -454,6 +467,8 @@ __global__ void __launch_bounds__(IB_THREADS, 2) img_bwd_kernel(const ImgK p) {
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
               facc[ci * 9 + kh * 3 + kw] = fmaf(c, src[ci * plane + kh * Wp + kw], facc[ci * 9 + kh * 3 + kw]);
+        jx[e] += 2 * (IB_THREADS / 32);
+        while (jx[e] >= p.wp) { jx[e] -= p.wp; ++jy[e]; }
       }
     }
     if ((++nb_done & 3) == 0) {
