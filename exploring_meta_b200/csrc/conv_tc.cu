@@ -61,6 +61,10 @@ struct ConvTcK {
   int stat_mode, accumulate;
   const float* src; const float* w; long long wstride;
   float* out; const float* aux; double* stats;
+  // channel blocking (64-channel layers run as 2 x 2 passes over 32-channel blocks): floats per position of the
+  // source / output tensors, first channel of this pass' block in each, and the weight block W[w_ao + a][w_bo + b]
+  // inside the task's [*][w_cin][3][3] tensor
+  int src_cs, src_co, out_cs, out_co, w_cin, w_ao, w_bo;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
@@ -98,8 +102,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   {
     const float* W = p.w + (long long)task * p.wstride;       // [co][ci][3][3]
     for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
-      const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[a][b][tap]
-      const float v = __ldg(W + i);
+      const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[w_ao + a][w_bo + b][tap]
+      const float v = __ldg(W + ((long long)(p.w_ao + a) * p.w_cin + p.w_bo + b) * 9 + tap);
       int n, k, t2;
       if (p.wmode == 0) { n = a; k = b; t2 = tap; }           // forward: n = cout, k = cin
       else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     // and stored, so the HBM/L2 latency overlaps the shared-memory phase and the wait for the stage.
     constexpr int PR = TC_PRODUCERS / 4;                       // rows staged per pass: a thread moves 8 channels
     const int c8 = tid & 3, jrow = tid >> 2;                   // channel octet (two planes), first row (0..PR-1)
-    const float* S = p.src + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
+    const float* S = p.src + (long long)task * p.n * p.H * p.W * p.src_cs + p.src_co + c8 * 8;
     auto issue_loads = [&](int it, float4 (&v)[8]) {
       const int qbase = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE - p.Wp - 1 + jrow;
 #pragma unroll
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         const int j = jrow + PR * u;
         const int px = j < p.R ? pos_to_pixel(p.pm, qbase + PR * u) : -1;
         v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (px >= 0) ldg256(S + (long long)px * 32, v[2 * u], v[2 * u + 1]);
+        if (px >= 0) ldg256(S + (long long)px * p.src_cs, v[2 * u], v[2 * u + 1]);
       }
     };
 #ifdef XM_TC_TIMING
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE + row;
       const int px = row < TC_TILE ? pos_to_pixel(p.pm, q) : -1;
       const bool valid = px >= 0;
-      const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * 32;
+      const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * p.out_cs + p.out_co;
       // tangent statistics multiply by one 128 B aux row per accumulator row: pull it into L1 while the warp waits
       // for the accumulators, so the loads in the epilogue do not expose HBM latency inside the drain
       if (p.stat_mode == XM_STAT_SUM_AUX && valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.aux + o));
@@ -458,9 +462,42 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
 // <0 / >0 on error like every entry point.
+// {sum v, sum v^2} per (task, channel) of an NHWC tensor, in double: BatchNorm statistics of the 64-channel layers,
+// whose output is accumulated over two input-channel passes (sum of squares is not additive over passes).
+__global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict__ z, long long pixels, int C, double* stats) {
+  extern __shared__ double cs_sh[];                       // [2][C]
+  const int task = blockIdx.y, c4n = C / 4, c4 = threadIdx.x % c4n, slot = threadIdx.x / c4n, slots = blockDim.x / c4n;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) cs_sh[i] = 0.0;
+  __syncthreads();
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+  float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* Z = reinterpret_cast<const float4*>(z + (long long)task * pixels * C) + c4;
+  int run = 0;
+  if (slot < slots)
+    for (long long px = (long long)blockIdx.x * slots + slot; px < pixels; px += (long long)gridDim.x * slots) {
+      const float4 v = __ldg(Z + px * c4n);
+      fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
+      fq[0] = fmaf(v.x, v.x, fq[0]); fq[1] = fmaf(v.y, v.y, fq[1]); fq[2] = fmaf(v.z, v.z, fq[2]); fq[3] = fmaf(v.w, v.w, fq[3]);
+      if ((++run & 15) == 0)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s[k] += (double)fs[k]; q[k] += (double)fq[k]; fs[k] = fq[k] = 0.f; }
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    atomicAdd(&cs_sh[4 * c4 + k], s[k] + (double)fs[k]);
+    atomicAdd(&cs_sh[C + 4 * c4 + k], q[k] + (double)fq[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(long long)task * 2 * C + i], cs_sh[i]);
+}
+
+// Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
+// <0 / >0 on error like every entry point.
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
-  if (g.cout != 32 || g.cin != 32 || g.stride != 1 || a->src_nchw) return 0;
+  if (g.stride != 1 || a->src_nchw || g.cin != g.cout || (g.cout != 32 && g.cout != 64)) return 0;
+  const int blocks = g.cout / 32;                            // 32-channel blocks per side
+  if (blocks > 1 && (a->src2 || a->stat_mode == XM_STAT_SUM_AUX)) return 0;   // tangent calls of wide layers: generic path
   if (a->src2 && a->stat_mode == XM_STAT_SUM_SQ) return 0;     // (sum of squares is not additive over the two passes)
   int R, plane_bytes;
   const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes);
@@ -473,6 +510,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   p.R = R; p.plane_bytes = plane_bytes;
   p.wmode = a->mode == XM_CONV_FWD ? 0 : 1;
   p.out = a->out; p.aux = a->aux; p.stats = a->stats;
+  p.src_cs = p.out_cs = p.w_cin = g.cout;
   int per_task = num_sms() / g.tasks;
   if (per_task < 1) per_task = 1;
   if (per_task > p.tiles_per_task) per_task = p.tiles_per_task;
@@ -482,16 +520,39 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * 32 * sizeof(double), stream));
-  const int npairs = a->src2 ? 2 : 1;
-  for (int pair = 0; pair < npairs; ++pair) {
-    p.src = pair ? a->src2 : a->src1;
-    p.w = pair ? a->w2 : a->w1;
-    p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
-    p.accumulate = pair;                                   // second pair adds onto the first pass' output
-    p.stat_mode = a->stat_mode;                            // {sum v, sum v*aux} are linear: each pass adds its share
-    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
-    if (int rc = launched("xm_conv(tcgen05)")) return rc;
+  if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * g.cout * sizeof(double), stream));
+  if (blocks == 1) {
+    const int npairs = a->src2 ? 2 : 1;
+    for (int pair = 0; pair < npairs; ++pair) {
+      p.src = pair ? a->src2 : a->src1;
+      p.w = pair ? a->w2 : a->w1;
+      p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
+      p.accumulate = pair;                                   // second pair adds onto the first pass' output
+      p.stat_mode = a->stat_mode;                            // {sum v, sum v*aux} are linear: each pass adds its share
+      conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+      if (int rc = launched("xm_conv(tcgen05)")) return rc;
+    }
+    return 1;
+  }
+  // 64 -> 64: output block ob gets the sum over source blocks sb of the 32 -> 32 convolution with weight block
+  // W[co block][ci block]; the second source block adds onto the first pass' output (vector red.add)
+  p.src = a->src1; p.w = a->w1; p.wstride = a->w1_task_stride;
+  p.stat_mode = XM_STAT_NONE;
+  for (int ob = 0; ob < blocks; ++ob)
+    for (int sb = 0; sb < blocks; ++sb) {
+      p.out_co = 32 * ob; p.src_co = 32 * sb;
+      p.w_ao = 32 * (p.wmode == 0 ? ob : sb);                // weight rows = output channels of the FORWARD conv
+      p.w_bo = 32 * (p.wmode == 0 ? sb : ob);
+      p.accumulate = sb;
+      conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+      if (int rc = launched("xm_conv(tcgen05, channel block)")) return rc;
+    }
+  if (a->stat_mode == XM_STAT_SUM_SQ) {
+    const long long pixels = (long long)g.n * g.hz * g.wz;
+    int nb = (2 * num_sms() + g.tasks - 1) / g.tasks;
+    if (nb < 1) nb = 1;
+    chan_stats_kernel<<<dim3(nb, g.tasks), 256, 2 * g.cout * sizeof(double), stream>>>(a->out, pixels, g.cout, a->stats);
+    if (int rc = launched("xm_conv(statistics)")) return rc;
   }
   return 1;
 }

@@ -328,7 +328,10 @@ static int wgrad_img_splits(const XmBlockGeom& g) {
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
                                     float* out_w, float* out_b, long long out_stride,
                                     const float* base_w, const float* base_b, long long base_stride,
-                                    float scale, int ctas = 0, int tiles_per_task = 0) {
+                                    float scale, int ctas = 0, int tiles_per_task = 0,
+                                    int cin_total = 0, int ci_off = 0, int co_off = 0) {
+  // (cin_total > 0: the partials are one 32 x 32 channel block of a wider layer's [cout][cin_total][3][3] gradient)
+  if (cin_total == 0) cin_total = cin;
   const int task = blockIdx.y;
   const int per = 9 * cin * cout;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,12 +348,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
     const float* P = partial + (long long)task * splits * per + i;
     double s = 0.0;
     for (int k = 0; k < used; ++k) s += (double)P[(long long)k * per];
-    const long long o = ((long long)co * cin + ci) * 9 + tap;
+    const long long o = ((long long)(co_off + co) * cin_total + ci_off + ci) * 9 + tap;
     const float b = base_w ? base_w[(long long)task * base_stride + o] : 0.f;
     out_w[(long long)task * out_stride + o] = b + scale * (float)s;
   }
   if (out_b && i < cout)
-    out_b[(long long)task * out_stride + i] = base_b ? base_b[(long long)task * base_stride + i] : 0.f;
+    out_b[(long long)task * out_stride + co_off + i] = base_b ? base_b[(long long)task * base_stride + co_off + i] : 0.f;
 }
 
 static void wgrad_geo(const XmBlockGeom& g, TileGeo& t) {
@@ -402,12 +405,18 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
     const int tsplits = wgrad_tc_try(a, stream, &rc, &tc_ctas, &tc_tiles);
     if (tsplits < 0) return rc;
     if (tsplits > 0) {
-      const int per = 9 * g.cin * g.cout;
+      const int per = 9 * 32 * 32, blocks = g.cout / 32;
       dim3 rgrid((per + 255) / 256, g.tasks);
-      wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, tsplits, g.cin, g.cout, a->out_w, a->out_b,
-                                                    a->out_task_stride, a->base_w, a->base_b,
-                                                    a->base_task_stride, a->scale, tc_ctas, tc_tiles);
-      return launched("xm_wgrad(reduce)");
+      for (int cb = 0; cb < blocks; ++cb)
+        for (int ib = 0; ib < blocks; ++ib) {
+          const float* part = a->partial + (long long)(cb * blocks + ib) * g.tasks * tsplits * per;
+          wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, tsplits, 32, 32, a->out_w, a->out_b,
+                                                        a->out_task_stride, a->base_w, a->base_b,
+                                                        a->base_task_stride, a->scale, tc_ctas, tc_tiles,
+                                                        g.cin, 32 * ib, 32 * cb);
+          if (int rc2 = launched("xm_wgrad(reduce)")) return rc2;
+        }
+      return 0;
     }
   }
   if (a->src_nchw && g.cin <= 4 && g.stride == 1 && !a->x2) {

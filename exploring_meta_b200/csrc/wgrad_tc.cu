@@ -39,6 +39,7 @@ struct WgradTcK {
   const float* x[2];
   const float* g[2];
   float* partial;                     // [task][split][9*32][32]
+  int x_cs, x_co, g_cs, g_co;         // floats per position of x / g and the first channel of this launch's 32-channel block
 };
 
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK p) {
@@ -145,21 +146,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       const int it = u / p.npairs, pair = u - it * p.npairs;
       const int gtile = g_lo + it, task = gtile / p.tiles_per_task;
       const int q0 = (gtile - task * p.tiles_per_task) * 128;
-      const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
-      const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * 32 + c8 * 8;
+      const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * p.x_cs + p.x_co + c8 * 8;
+      const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * p.g_cs + p.g_co + c8 * 8;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int j = jrow + PR * k;
         const int px = j < p.Rx ? pos_to_pixel(p.pm, q0 - 1 + j) : -1;
         r.x[2 * k] = r.x[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (px >= 0) ldg256(X + (long long)px * 32, r.x[2 * k], r.x[2 * k + 1]);
+        if (px >= 0) ldg256(X + (long long)px * p.x_cs, r.x[2 * k], r.x[2 * k + 1]);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = jrow + PR * k;
         const int px = i < p.Rg ? pos_to_pixel(p.pm, q0 - p.Wp + i) : -1;
         r.g[2 * k] = r.g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (px >= 0) ldg256(G + (long long)px * 32, r.g[2 * k], r.g[2 * k + 1]);
+        if (px >= 0) ldg256(G + (long long)px * p.g_cs, r.g[2 * k], r.g[2 * k + 1]);
       }
     };
     auto store = [&](int u, const Regs& r) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 }
 
 static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
-  if (g.cin != 32 || g.cout != 32 || g.stride != 1) return false;
+  if (g.cin != g.cout || (g.cout != 32 && g.cout != 64) || g.stride != 1) return false;
   p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
   p.Q = g.n * p.Hp * p.Wp;
   p.pm = make_posmap(g.n, g.hin, g.win);
@@ -277,7 +278,8 @@ long long wgrad_tc_partial_floats(const XmBlockGeom& g) {
   WgradTcK p{};
   size_t smem;
   if (!wgrad_tc_layout(g, p, smem)) return 0;
-  return (long long)g.tasks * p.splits * 9 * 32 * 32;
+  const int blocks = g.cout / 32;                      // 64-channel layers: one launch per (cout block, cin block)
+  return (long long)blocks * blocks * g.tasks * p.splits * 9 * 32 * 32;
 }
 
 // Returns the number of partial slots per task in a->partial (>0) when handled (slot j of task t is written by CTA
@@ -287,6 +289,7 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   const XmBlockGeom& g = a->g;
   *rc_out = 0;
   if (a->src_nchw) return 0;
+  if (g.cout != 32 && a->x2) return 0;                 // tangent calls of wide layers: generic path
   WgradTcK p{};
   size_t smem;
   if (!wgrad_tc_layout(g, p, smem)) return 0;
@@ -300,8 +303,17 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
     if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
   }
-  wgrad_tc_kernel<<<p.ctas, WT_THREADS, smem, stream>>>(p);
-  if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
+  // block (cb, ib) of a wide layer: gW[32 cb .. +31][32 ib .. +31] from g's channel block cb and x's channel block ib,
+  // into partial region cb * blocks + ib
+  const int blocks = g.cout / 32;
+  p.x_cs = p.g_cs = g.cout;
+  for (int cb = 0; cb < blocks; ++cb)
+    for (int ib = 0; ib < blocks; ++ib) {
+      p.g_co = 32 * cb; p.x_co = 32 * ib;
+      p.partial = a->partial + (long long)(cb * blocks + ib) * g.tasks * p.splits * 9 * 32 * 32;
+      wgrad_tc_kernel<<<p.ctas, WT_THREADS, smem, stream>>>(p);
+      if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
+    }
   *ctas_out = p.ctas;
   *tiles_out = p.tiles_per_task;
   return p.splits;
