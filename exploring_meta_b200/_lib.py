@@ -26,7 +26,8 @@ class XmConvArgs(Structure):
                 ('stat_mode', c_int32),
                 ('src1', c_void_p), ('w1', c_void_p), ('w1_task_stride', c_int64),
                 ('src2', c_void_p), ('w2', c_void_p), ('w2_task_stride', c_int64),
-                ('out', c_void_p), ('aux', c_void_p), ('stats', c_void_p)]
+                ('out', c_void_p), ('aux', c_void_p), ('stats', c_void_p),
+                ('workspace', c_void_p), ('workspace_bytes', c_int64)]
 
 
 class XmWgradArgs(Structure):
@@ -99,6 +100,7 @@ class XmAnilHeadArgs(Structure):
 # name -> (restype, argtypes): every symbol include/xmeta.h declares.
 SYMBOLS = {
     'xm_conv': (c_int32, [POINTER(XmConvArgs), c_void_p]),
+    'xm_conv_workspace_bytes': (c_int64, [POINTER(XmBlockGeom)]),
     'xm_wgrad_scratch_bytes': (c_int64, [POINTER(XmBlockGeom)]),
     'xm_wgrad': (c_int32, [POINTER(XmWgradArgs), c_void_p]),
     'xm_bn_scratch_bytes': (c_int64, [POINTER(XmBlockGeom)]),

@@ -249,6 +249,7 @@ conv_kernel(const ConvK p) {
 int g_precise = 1;
 int g_use_tc = 1;
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream);
+long long conv_tc_workspace_floats(const XmBlockGeom& g);
 int conv_img_try(const XmConvArgs* a, cudaStream_t stream);
 
 }  // namespace xm
@@ -263,6 +264,11 @@ extern "C" int xm_set_precision(int precise) {
 extern "C" int xm_set_tcgen05(int enable) {
   g_use_tc = enable;
   return 0;
+}
+
+extern "C" int64_t xm_conv_workspace_bytes(const XmBlockGeom* g) {
+  if (!g || !geom_ok(*g)) return -1;
+  return conv_tc_workspace_floats(*g) * (int64_t)sizeof(float);
 }
 
 extern "C" int xm_conv(const XmConvArgs* a, void* stream_) {

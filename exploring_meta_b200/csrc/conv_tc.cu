@@ -464,7 +464,9 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
 // <0 / >0 on error like every entry point.
 // {sum v, sum v^2} per (task, channel) of an NHWC tensor, in double: BatchNorm statistics of the 64-channel layers,
 // whose output is accumulated over two input-channel passes (sum of squares is not additive over passes).
-__global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict__ z, long long pixels, int C, double* stats) {
+// aux != NULL: {sum v, sum v*aux} (tangent statistics).
+__global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict__ z, long long pixels, int C, double* stats,
+                                                         const float* __restrict__ aux) {
   extern __shared__ double cs_sh[];                       // [2][C]
   const int task = blockIdx.y, c4n = C / 4, c4 = threadIdx.x % c4n, slot = threadIdx.x / c4n, slots = blockDim.x / c4n;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) cs_sh[i] = 0.0;
@@ -472,12 +474,13 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict
   double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
   float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
   const float4* Z = reinterpret_cast<const float4*>(z + (long long)task * pixels * C) + c4;
+  const float4* A = aux ? reinterpret_cast<const float4*>(aux + (long long)task * pixels * C) + c4 : Z;
   int run = 0;
   if (slot < slots)
     for (long long px = (long long)blockIdx.x * slots + slot; px < pixels; px += (long long)gridDim.x * slots) {
-      const float4 v = __ldg(Z + px * c4n);
+      const float4 v = __ldg(Z + px * c4n), w = __ldg(A + px * c4n);
       fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
-      fq[0] = fmaf(v.x, v.x, fq[0]); fq[1] = fmaf(v.y, v.y, fq[1]); fq[2] = fmaf(v.z, v.z, fq[2]); fq[3] = fmaf(v.w, v.w, fq[3]);
+      fq[0] = fmaf(v.x, w.x, fq[0]); fq[1] = fmaf(v.y, w.y, fq[1]); fq[2] = fmaf(v.z, w.z, fq[2]); fq[3] = fmaf(v.w, w.w, fq[3]);
       if ((++run & 15) == 0)
 #pragma unroll
         for (int k = 0; k < 4; ++k) { s[k] += (double)fs[k]; q[k] += (double)fq[k]; fs[k] = fq[k] = 0.f; }
@@ -491,14 +494,65 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(long long)task * 2 * C + i], cs_sh[i]);
 }
 
+// Stride-2 layers on the stride-1 kernels: conv_s2(x)[r][c] = conv_s1(x)[2r][2c] (forward: full-resolution pass into
+// the workspace, then sub-sampling), and the data gradient of conv_s2 is the stride-1 data gradient of the cotangent
+// with zeros inserted between its elements.  4x the arithmetic of a native stride-2 kernel, on a path ~40x faster.
+__global__ void subsample2_kernel(const float4* __restrict__ full, float4* __restrict__ out, long long imgs, int H, int W,
+                                  int hz, int wz, int c4n) {
+  const long long total = imgs * hz * wz * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n);
+    long long r = i / c4n;
+    const int x = (int)(r % wz); r /= wz;
+    const int y = (int)(r % hz);
+    const long long img = r / hz;
+    out[i] = __ldg(full + ((img * H + 2 * y) * W + 2 * x) * c4n + c);
+  }
+}
+__global__ void upsample2_kernel(const float4* __restrict__ src, float4* __restrict__ full, long long imgs, int H, int W,
+                                 int hz, int wz, int c4n) {
+  const long long total = imgs * H * W * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n);
+    long long r = i / c4n;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const long long img = r / H;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(x & 1) && !(y & 1) && (y >> 1) < hz && (x >> 1) < wz) v = __ldg(src + ((img * hz + (y >> 1)) * wz + (x >> 1)) * c4n + c);
+    full[i] = v;
+  }
+}
+
+// host-side launcher shared with wgrad_tc.cu
+int launch_upsample2(const float* src, float* full, long long imgs, int H, int W, int hz, int wz, int C, cudaStream_t stream) {
+  const long long total = imgs * H * W * (C / 4);
+  const int nb = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+  upsample2_kernel<<<nb, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(full), imgs, H, W,
+                                           hz, wz, C / 4);
+  return launched("zero insertion (stride 2)");
+}
+
+static bool conv_tc_covers(const XmBlockGeom& g) {
+  return g.cin == g.cout && (g.cout == 32 || g.cout == 64) && (g.stride == 1 || g.stride == 2);
+}
+long long conv_tc_workspace_floats(const XmBlockGeom& g) {
+  if (!conv_tc_covers(g) || g.stride != 2) return 0;
+  return (long long)g.tasks * g.n * g.hin * g.win * g.cout;       // one full-resolution tensor
+}
+
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
 // <0 / >0 on error like every entry point.
 int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
-  if (g.stride != 1 || a->src_nchw || g.cin != g.cout || (g.cout != 32 && g.cout != 64)) return 0;
+  if (a->src_nchw || !conv_tc_covers(g)) return 0;
   const int blocks = g.cout / 32;                            // 32-channel blocks per side
-  if (blocks > 1 && (a->src2 || a->stat_mode == XM_STAT_SUM_AUX)) return 0;   // tangent calls of wide layers: generic path
-  if (a->src2 && a->stat_mode == XM_STAT_SUM_SQ) return 0;     // (sum of squares is not additive over the two passes)
+  const bool s2 = g.stride == 2;
+  if (s2 && (!a->workspace || a->workspace_bytes < conv_tc_workspace_floats(g) * 4)) return 0;
+  // statistics in the drain need ONE pass per output element and (sum of squares) one (src, w) pair; otherwise a
+  // streaming pass over the finished output computes them
+  const bool multi = blocks > 1 || s2;
+  if (!multi && a->src2 && a->stat_mode == XM_STAT_SUM_SQ) return 0;
   int R, plane_bytes;
   const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes);
   if (smem > 227 * 1024 || R > TC_PRODUCERS) return 0;      // each producer thread stages <= 4 rows per tile
@@ -521,8 +575,8 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     attr_set = true;
   }
   if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * g.cout * sizeof(double), stream));
-  if (blocks == 1) {
-    const int npairs = a->src2 ? 2 : 1;
+  const int npairs = a->src2 ? 2 : 1;
+  if (!multi) {
     for (int pair = 0; pair < npairs; ++pair) {
       p.src = pair ? a->src2 : a->src1;
       p.w = pair ? a->w2 : a->w1;
@@ -534,24 +588,46 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     }
     return 1;
   }
-  // 64 -> 64: output block ob gets the sum over source blocks sb of the 32 -> 32 convolution with weight block
-  // W[co block][ci block]; the second source block adds onto the first pass' output (vector red.add)
-  p.src = a->src1; p.w = a->w1; p.wstride = a->w1_task_stride;
+  // Channel-block passes (64 -> 64: output block ob = sum over source blocks sb of the 32 -> 32 convolution with weight
+  // block W[co block][ci block]) and / or stride 2.  Every pass after the first into an output block accumulates with
+  // vector red.add.
+  const long long imgs = (long long)g.tasks * g.n;
+  const int c4n = g.cout / 4;
+  const bool fwd = p.wmode == 0;
   p.stat_mode = XM_STAT_NONE;
-  for (int ob = 0; ob < blocks; ++ob)
-    for (int sb = 0; sb < blocks; ++sb) {
-      p.out_co = 32 * ob; p.src_co = 32 * sb;
-      p.w_ao = 32 * (p.wmode == 0 ? ob : sb);                // weight rows = output channels of the FORWARD conv
-      p.w_bo = 32 * (p.wmode == 0 ? sb : ob);
-      p.accumulate = sb;
-      conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
-      if (int rc = launched("xm_conv(tcgen05, channel block)")) return rc;
+  p.out = (s2 && fwd) ? a->workspace : a->out;             // stride-2 forward: full-resolution result first
+  for (int pair = 0; pair < npairs; ++pair) {
+    const float* src = pair ? a->src2 : a->src1;
+    if (s2 && !fwd) {                                      // stride-2 data gradient: zero-inserted cotangent
+      if (int rc = launch_upsample2(src, a->workspace, imgs, g.hin, g.win, g.hz, g.wz, g.cout, stream)) return rc;
+      src = a->workspace;
     }
-  if (a->stat_mode == XM_STAT_SUM_SQ) {
-    const long long pixels = (long long)g.n * g.hz * g.wz;
+    p.src = src;
+    p.w = pair ? a->w2 : a->w1;
+    p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
+    for (int ob = 0; ob < blocks; ++ob)
+      for (int sb = 0; sb < blocks; ++sb) {
+        p.out_co = 32 * ob; p.src_co = 32 * sb;
+        p.w_ao = 32 * (fwd ? ob : sb);                     // weight rows = output channels of the FORWARD conv
+        p.w_bo = 32 * (fwd ? sb : ob);
+        p.accumulate = (pair > 0 || sb > 0) ? 1 : 0;
+        conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+        if (int rc = launched("xm_conv(tcgen05, channel block)")) return rc;
+      }
+  }
+  long long out_pixels = (long long)g.n * g.hin * g.win;
+  if (s2 && fwd) {
+    const long long total = imgs * g.hz * g.wz * c4n;
+    subsample2_kernel<<<(int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(a->workspace), reinterpret_cast<float4*>(a->out), imgs, g.hin, g.win, g.hz, g.wz, c4n);
+    if (int rc = launched("xm_conv(sub-sampling)")) return rc;
+    out_pixels = (long long)g.n * g.hz * g.wz;
+  }
+  if (a->stat_mode) {
     int nb = (2 * num_sms() + g.tasks - 1) / g.tasks;
     if (nb < 1) nb = 1;
-    chan_stats_kernel<<<dim3(nb, g.tasks), 256, 2 * g.cout * sizeof(double), stream>>>(a->out, pixels, g.cout, a->stats);
+    chan_stats_kernel<<<dim3(nb, g.tasks), 256, 2 * g.cout * sizeof(double), stream>>>(
+        a->out, out_pixels, g.cout, a->stats, a->stat_mode == XM_STAT_SUM_AUX ? a->aux : nullptr);
     if (int rc = launched("xm_conv(statistics)")) return rc;
   }
   return 1;

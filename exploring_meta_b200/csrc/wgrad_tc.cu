@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 }
 
 static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
-  if (g.cin != g.cout || (g.cout != 32 && g.cout != 64) || g.stride != 1) return false;
+  if (g.cin != g.cout || (g.cout != 32 && g.cout != 64) || (g.stride != 1 && g.stride != 2)) return false;
   p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
   p.Q = g.n * p.Hp * p.Wp;
   p.pm = make_posmap(g.n, g.hin, g.win);
@@ -279,8 +279,13 @@ long long wgrad_tc_partial_floats(const XmBlockGeom& g) {
   size_t smem;
   if (!wgrad_tc_layout(g, p, smem)) return 0;
   const int blocks = g.cout / 32;                      // 64-channel layers: one launch per (cout block, cin block)
-  return (long long)blocks * blocks * g.tasks * p.splits * 9 * 32 * 32;
+  long long floats = (long long)blocks * blocks * g.tasks * p.splits * 9 * 32 * 32;
+  if (g.stride == 2) floats += 2LL * g.tasks * g.n * g.hin * g.win * g.cout;   // zero-inserted cotangents (two pairs)
+  return floats;
 }
+
+// (conv_tc.cu) full[img][y][x] = (x, y even) ? src[img][y/2][x/2] : 0
+int launch_upsample2(const float* src, float* full, long long imgs, int H, int W, int hz, int wz, int C, cudaStream_t stream);
 
 // Returns the number of partial slots per task in a->partial (>0) when handled (slot j of task t is written by CTA
 // first(t) + j of the persistent grid; wgrad_reduce_kernel derives each task's slot count from *ctas_out and
@@ -289,7 +294,6 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   const XmBlockGeom& g = a->g;
   *rc_out = 0;
   if (a->src_nchw) return 0;
-  if (g.cout != 32 && a->x2) return 0;                 // tangent calls of wide layers: generic path
   WgradTcK p{};
   size_t smem;
   if (!wgrad_tc_layout(g, p, smem)) return 0;
@@ -307,6 +311,16 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   // into partial region cb * blocks + ib
   const int blocks = g.cout / 32;
   p.x_cs = p.g_cs = g.cout;
+  if (g.stride == 2) {
+    // stride-2 weight gradient = stride-1 weight gradient against the cotangent with zeros inserted between its
+    // elements (full input resolution); the copies live behind the partial blocks in the scratch buffer
+    float* up = a->partial + (long long)blocks * blocks * g.tasks * p.splits * 9 * 32 * 32;
+    const long long imgs = (long long)g.tasks * g.n, per = imgs * g.hin * g.win * g.cout;
+    for (int pair = 0; pair < p.npairs; ++pair) {
+      if (int rc = launch_upsample2(p.g[pair], up + pair * per, imgs, g.hin, g.win, g.hz, g.wz, g.cout, stream)) { *rc_out = rc; return -1; }
+      p.g[pair] = up + pair * per;
+    }
+  }
   for (int cb = 0; cb < blocks; ++cb)
     for (int ib = 0; ib < blocks; ++ib) {
       p.g_co = 32 * cb; p.x_co = 32 * ib;

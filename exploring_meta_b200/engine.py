@@ -44,11 +44,14 @@ def _p(t, off=0):
 class _Program:
     """A recorded list of C-ABI calls: (function, argument block)."""
 
-    def __init__(self, lib):
+    def __init__(self, lib, conv_ws=None):
         self.lib = lib
         self.calls = []
+        self.conv_ws = conv_ws          # workspace handed to every xm_conv call (stride-2 layers on the tcgen05 path)
 
     def emit(self, name, args):
+        if name == 'xm_conv' and self.conv_ws is not None:
+            args.workspace, args.workspace_bytes = _p(self.conv_ws), self.conv_ws.numel() * 4
         self.calls.append((getattr(self.lib, name), args, name))
 
     def emit_raw(self, name, *argv):
@@ -105,6 +108,8 @@ class _EngineBase:
         self.bn_scratch = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=self.device)
         wbytes = max(int(self.lib.xm_wgrad_scratch_bytes(ctypes.byref(self.geom(l, nmax)))) for l in range(L))
         self.wg_partial = torch.empty(max(wbytes, 4) // 4, dtype=torch.float32, device=self.device)
+        cbytes = max(int(self.lib.xm_conv_workspace_bytes(ctypes.byref(self.geom(l, nmax)))) for l in range(L))
+        self.conv_ws = torch.empty(max(cbytes, 4) // 4, dtype=torch.float32, device=self.device) if cbytes > 0 else None
         del g0
         # fused image block (xm_img_*): first ConvBlock without ever writing its pre-BN map (csrc/img_block.cu)
         g = self.geom(0, nmax)
@@ -254,7 +259,7 @@ class _EngineBase:
     def rebuild(self):
         """Re-records the launch program (after a caller re-pointed ``theta`` / ``grad`` at its own
         buffers) and drops any captured graph."""
-        self.prog = _Program(self.lib)
+        self.prog = _Program(self.lib, self.conv_ws)
         self._graph = None
         self._build()
 
@@ -315,7 +320,7 @@ class MamlEngine(_EngineBase):
         self.GZ = self._f32(zmax)
         self.GZdot = self._f32(zmax) if mode == 'second' else None
         self.bar = [self._f32(B, P), self._f32(B, P)] if mode != 'eval' else None
-        self.prog = _Program(self.lib)
+        self.prog = _Program(self.lib, self.conv_ws)
         self._build()
 
     # theta_t as (tensor, task stride): theta_0 is the shared master vector
@@ -548,7 +553,7 @@ class AnilEngine(_EngineBase):
         self.GZ = self._f32(max([self.Z[l].numel() for l in range(l0, L)] or [1]))
         self.task_grad = self._f32(B, P)
         self.task_head_grad = self._f32(B, self.PH)
-        self.prog = _Program(self.lib)
+        self.prog = _Program(self.lib, self.conv_ws)
         self._build()
 
     def _build(self):

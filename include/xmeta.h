@@ -77,7 +77,11 @@ typedef struct XmConvArgs {
   float* out;
   const float* aux;                       /* SUM_AUX: tensor shaped like out           */
   double* stats;
+  float* workspace; int64_t workspace_bytes;   /* optional, >= xm_conv_workspace_bytes(&g): lets stride-2 layers run on
+                                             the tcgen05 kernels (full-resolution pass + sub-sampling / zero insertion);
+                                             NULL = the generic kernels                */
 } XmConvArgs;
+int64_t xm_conv_workspace_bytes(const XmBlockGeom* g);
 int xm_conv(const XmConvArgs* a, void* stream);
 
 /* xm_wgrad: weight gradient gW[co][ci][kh][kw] = sum_{n,h,w} x[n, s*h+kh-1, s*w+kw-1, ci] * g[n,h,w,co]

@@ -137,6 +137,9 @@ class EmulatedLib:
         g = self._args(ref)
         return g.tasks * 4 * g.cout * 8
 
+    def xm_conv_workspace_bytes(self, ref):
+        return 0
+
     def xm_wgrad_scratch_bytes(self, ref):
         g = self._args(ref)
         return g.tasks * 9 * g.cin * g.cout * 4

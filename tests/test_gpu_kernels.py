@@ -92,10 +92,14 @@ def test_conv_forward(case, dual):
     P.add('w', torch.randn(tasks, cout, cin, 3, 3) * 0.2).add('wd', torch.randn(tasks, cout, cin, 3, 3) * 0.2)
     P.add('aux', torch.randn(tasks, n, g.hz, g.wz, cout))
     P.out('out', (tasks, n, g.hz, g.wz, cout)).out('stats', (tasks, 2, cout), torch.float64)
+    ws_bytes = max(int(_lib.load().xm_conv_workspace_bytes(ctypes.byref(g))), 0)   # stride-2 layers on the tcgen05 path
+    P.out('ws', (max(ws_bytes // 4, 1),))
 
     def mk(ptr):
         a = XmConvArgs()
         a.g, a.mode = g, 0
+        if ws_bytes:
+            a.workspace, a.workspace_bytes = ptr('ws'), ws_bytes
         a.stat_mode = 2 if dual else 1
         if nchw:
             a.src_nchw, a.row0, a.row_step, a.rows_per_task = 1, 1, 2, rows
@@ -119,10 +123,14 @@ def test_conv_dgrad(case, dual):
     P.add('gz', torch.randn(tasks, n, g.hz, g.wz, cout)).add('gzd', torch.randn(tasks, n, g.hz, g.wz, cout))
     P.add('w', torch.randn(tasks, cout, cin, 3, 3) * 0.2).add('wd', torch.randn(tasks, cout, cin, 3, 3) * 0.2)
     P.out('out', (tasks, n, hin, hin, cin))
+    ws_bytes = max(int(_lib.load().xm_conv_workspace_bytes(ctypes.byref(g))), 0)
+    P.out('ws', (max(ws_bytes // 4, 1),))
 
     def mk(ptr):
         a = XmConvArgs()
         a.g, a.mode, a.stat_mode = g, 1, 0
+        if ws_bytes:
+            a.workspace, a.workspace_bytes = ptr('ws'), ws_bytes
         a.src1, a.w1, a.w1_task_stride = ptr('gz'), ptr('w'), cout * cin * 9
         if dual:
             a.src2, a.w2, a.w2_task_stride = ptr('gzd'), ptr('wd'), cout * cin * 9
