@@ -5,7 +5,7 @@ that computes anything goes through ``load()``.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_double, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libxmeta.so')
@@ -73,6 +73,15 @@ class XmImgArgs(Structure):
                 ('base_task_stride', c_int64)]
 
 
+class XmSampleArgs(Structure):
+    _fields_ = [('tasks', c_int32), ('ways', c_int32), ('shots2', c_int32), ('channels', c_int32),
+                ('height', c_int32), ('width', c_int32), ('num_classes', c_int32), ('rotate', c_int32),
+                ('seed', c_uint64), ('first_task', c_int64),
+                ('data', c_void_p), ('class_start', c_void_p),
+                ('scale', c_float), ('offset', c_float),
+                ('x', c_void_p), ('y', c_void_p), ('items', c_void_p), ('classes', c_void_p)]
+
+
 class XmHeadArgs(Structure):
     _fields_ = [('tasks', c_int32), ('n', c_int32), ('ways', c_int32), ('c', c_int32), ('hw', c_int32),
                 ('mode', c_int32), ('dual', c_int32),
@@ -119,6 +128,7 @@ SYMBOLS = {
     'xm_head': (c_int32, [POINTER(XmHeadArgs), c_void_p]),
     'xm_anil_head_scratch_bytes': (c_int64, [POINTER(XmAnilHeadArgs)]),
     'xm_anil_head': (c_int32, [POINTER(XmAnilHeadArgs), c_void_p]),
+    'xm_sample_tasks': (c_int32, [POINTER(XmSampleArgs), c_void_p]),
     'xm_accumulate_tasks': (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p]),
     'xm_adam_step': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                c_float, c_float, c_float, c_int32, c_void_p]),

@@ -232,6 +232,25 @@ typedef struct XmAnilHeadArgs {
 int64_t xm_anil_head_scratch_bytes(const XmAnilHeadArgs* a);
 int xm_anil_head(const XmAnilHeadArgs* a, void* stream);
 
+/* xm_sample_tasks: on-device few-shot task sampler over a dataset resident in HBM as uint8: what
+ * train_tasks.sample() yields in the reference -- learn2learn's NWays -> KShots(2k) -> LoadData -> RemapLabels ->
+ * ConsecutiveLabels (-> RandomClassRotation) chain of utils/data_pre.py:28-37,79-85 -- for `tasks` tasks at once:
+ *   x[t][ways*shots2][C][H][W] = scale * u8 + offset, samples grouped by class, one quarter-turn rotation per class
+ *   of the task when `rotate`;  y[t][ways*shots2] = 0..ways-1, each shots2 times.
+ * Items of class c are data[class_start[c] .. class_start[c+1]) (every class needs >= shots2 items).  Draws are
+ * counter based (splitmix64 of seed, first_task + t, draw counter): a batch is a pure function of (seed, first_task);
+ * oracle/task_sampler_oracle.py restates the algorithm bit for bit.  items / classes (optional) return the chosen
+ * item indices [t][ways*shots2] and class ids [t][ways]. */
+typedef struct XmSampleArgs {
+  int32_t tasks, ways, shots2, channels, height, width, num_classes, rotate;
+  uint64_t seed; int64_t first_task;
+  const uint8_t* data; const int32_t* class_start;
+  float scale, offset;
+  float* x; int64_t* y;
+  int32_t* items; int32_t* classes;
+} XmSampleArgs;
+int xm_sample_tasks(const XmSampleArgs* a, void* stream);
+
 /* dst[i] = (accumulate ? dst[i] : 0) + sum_t src[t*task_stride + i], tasks added in order in fp32 --
  * the order in which eval_loss.backward() accumulates into the master .grad (vision/maml_vision.py:112). */
 int xm_accumulate_tasks(const float* src, int64_t task_stride, int32_t tasks, int64_t count,

@@ -577,6 +577,26 @@ class EmulatedLib:
         write_param(a.g_b, a.g_task_stride, B, bb)
         return 0
 
+    # ------------------------------------------------------------------ on-device task sampler
+    def xm_sample_tasks(self, ref, stream):
+        from oracle import task_sampler_oracle as tso
+        a = self._args(ref)
+        self.launches += 1
+        cs = view(a.class_start, (a.num_classes + 1,), torch.int32).numpy()
+        n_items = int(cs[-1])
+        data = view(a.data, (n_items, a.channels, a.height, a.width), torch.uint8).numpy()
+        seed = a.seed & ((1 << 64) - 1)
+        x, y, items, classes = tso.sample_tasks(data, cs, a.tasks, a.ways, a.shots2, seed, a.first_task,
+                                                rotate=bool(a.rotate), scale=a.scale, offset=a.offset)
+        per = a.ways * a.shots2
+        view(a.x, x.shape).copy_(torch.from_numpy(x))
+        view(a.y, (a.tasks, per), torch.int64).copy_(torch.from_numpy(y))
+        if a.items:
+            view(a.items, (a.tasks, per), torch.int32).copy_(torch.from_numpy(items))
+        if a.classes:
+            view(a.classes, (a.tasks, a.ways), torch.int32).copy_(torch.from_numpy(classes))
+        return 0
+
     # ------------------------------------------------------------------ outer-step helpers
     def xm_accumulate_tasks(self, src, task_stride, tasks, count, dst, accumulate, stream):
         self.launches += 1
