@@ -24,7 +24,7 @@
 // Reference ops replaced: conv2d / native_batch_norm / relu / max_pool2d_with_indices of the first ConvBlock
 // (core_functions/vision_models.py:188-193), their backward and double-backward ops (vision/maml_vision.py:112) and
 // the fused SGD step of learn2learn's maml_update for this block's four parameters.
-#include "common.cuh"
+#include "img_flat.cuh"
 
 namespace xm {
 
@@ -33,23 +33,6 @@ constexpr int IB_ROWS = 6;          // z rows per band of the forward (3 pooled 
 constexpr int IB_PROWS = 3;         // pooled rows per band of the backward
 constexpr int GR_ROWS = 8;          // image rows per band of the Gram kernel (= workers per pair)
 
-struct ImgK {
-  int n, H, W, cout, splits, hp, wp;
-  int row0, row_step, rows_per_task;
-  double cnt;
-  float eps, scale;
-  const float* x; double* gram;
-  const float* w; long long wstride;
-  const float* wd; long long wdstride;
-  const float* gamma; const float* beta; long long gbstride;
-  const float* gammad; const float* betad; long long gbdstride;
-  float* mean_invstd; float* call_stats; float* bwd_red; float* dual_red;
-  float* p; float* zsel; unsigned char* sel; float* pdot; float* zdsel;
-  const float* gp; const float* gpd;
-  double* ssum; double* scratch;
-  float* out_w; float* out_b; float* out_gamma; float* out_beta; long long ostride;
-  const float* base_w; const float* base_b; const float* base_gamma; const float* base_beta; long long bstride;
-};
 
 __device__ __forceinline__ const float* image_ptr(const ImgK& p, int task, int img, int cin) {
   return p.x + ((long long)task * p.rows_per_task + p.row0 + (long long)img * p.row_step) * cin * p.H * p.W;
@@ -583,10 +566,11 @@ __global__ void __launch_bounds__(256) img_finalize_kernel(const ImgK p) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static int img_ok(const XmBlockGeom& g) {
+static int pooled_ok(const XmBlockGeom& g) {
   return geom_ok(g) && g.cin >= 1 && g.cin <= 4 && g.stride == 1 && g.pool == 1 && g.hz % 2 == 0 && g.wz % 2 == 0 &&
          g.cout % 32 == 0 && g.cout <= 1024;
 }
+static int img_ok(const XmBlockGeom& g) { return pooled_ok(g) || flat_ok(g); }
 
 static void fill(const XmImgArgs* a, ImgK& k) {
   const XmBlockGeom& g = a->g;
@@ -609,7 +593,7 @@ static void fill(const XmImgArgs* a, ImgK& k) {
 static int common_checks(const XmImgArgs* a, const char* who) {
   XM_REQUIRE(a != nullptr, "%s: null args", who);
   XM_REQUIRE(img_ok(a->g), "%s: geometry not covered by the image-block path (need cin <= 4, stride 1, 2x2 pool, even "
-             "hz/wz, cout %% 32 == 0); use xm_conv / xm_bn_* / xm_wgrad", who);
+             "hz/wz, cout %% 32 == 0 -- or cin 1, stride 2, no pool, cout 32 / 64); use xm_conv / xm_bn_* / xm_wgrad", who);
   XM_REQUIRE(a->x && a->gram, "%s: null x/gram", who);
   XM_REQUIRE(a->row_step >= 1 && a->row0 >= 0 && a->row0 + (int64_t)(a->g.n - 1) * a->row_step < a->rows_per_task,
              "%s: image row selection out of range", who);
@@ -661,6 +645,9 @@ static int launch_fwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
 }
 
 template <int CIN, int DUAL>
+static int launch_finalize(const XmImgArgs* a, ImgK& k, cudaStream_t stream);
+
+template <int CIN, int DUAL>
 static int launch_bwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   constexpr int K = 9 * CIN, NA = K + 3;
   const XmBlockGeom& g = a->g;
@@ -677,6 +664,13 @@ static int launch_bwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   XM_CUDA(cudaMemsetAsync(a->scratch, 0, (size_t)g.tasks * g.cout * NA * sizeof(double), stream));
   img_bwd_kernel<CIN, DUAL><<<dim3(splits, g.tasks, cotiles), IB_THREADS, smem, stream>>>(k);
   if (int rc = launched(DUAL ? "xm_img_dual_bwd(gather)" : "xm_img_bwd(gather)")) return rc;
+  return launch_finalize<CIN, DUAL>(a, k, stream);
+}
+
+template <int CIN, int DUAL>
+static int launch_finalize(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
+  constexpr int K = 9 * CIN;
+  const XmBlockGeom& g = a->g;
   const size_t fsmem = ((size_t)K * K + K + (size_t)(DUAL ? 4 : 2) * g.cout * K) * sizeof(double);
   XM_REQUIRE(fsmem <= 200 * 1024, "xm_img_bwd: too many channels for the finalize kernel");
   static bool fattr = false;
@@ -706,6 +700,7 @@ extern "C" int xm_img_gram(const XmImgArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = common_checks(a, "xm_img_gram")) return rc;
   ImgK k; fill(a, k);
+  if (flat_ok(a->g)) return flat_launch_gram(a, k, stream);
   int rc = 0;
   IMG_DISPATCH(a->g.cin, rc = launch_gram<CIN>(a, k, stream));
   return rc;
@@ -714,9 +709,11 @@ extern "C" int xm_img_gram(const XmImgArgs* a, void* stream_) {
 extern "C" int xm_img_fwd(const XmImgArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = common_checks(a, "xm_img_fwd")) return rc;
-  XM_REQUIRE(a->w && a->gamma && a->beta && a->mean_invstd && a->p && a->zsel && a->sel,
+  const bool flat = flat_ok(a->g);
+  XM_REQUIRE(a->w && a->gamma && a->beta && a->mean_invstd && a->p && (flat || (a->zsel && a->sel)),
              "xm_img_fwd: null w/gamma/beta/mean_invstd/p/zsel/sel");
   ImgK k; fill(a, k);
+  if (flat) return flat_launch(0, a, k, stream);
   int rc = 0;
   IMG_DISPATCH(a->g.cin, (rc = launch_fwd<CIN, 0>(a, k, stream)));
   return rc;
@@ -725,10 +722,12 @@ extern "C" int xm_img_fwd(const XmImgArgs* a, void* stream_) {
 extern "C" int xm_img_dual_fwd(const XmImgArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = common_checks(a, "xm_img_dual_fwd")) return rc;
-  XM_REQUIRE(a->w && a->w_dot && a->gamma && a->gamma_dot && a->beta_dot && a->mean_invstd && a->dual_red && a->zsel &&
-             a->sel && a->pdot && a->zdsel,
-             "xm_img_dual_fwd: null w/w_dot/gamma/gamma_dot/beta_dot/mean_invstd/dual_red/zsel/sel/pdot/zdsel");
+  const bool flat = flat_ok(a->g);
+  XM_REQUIRE(a->w && a->w_dot && a->gamma && a->gamma_dot && a->beta_dot && a->mean_invstd && a->dual_red && a->pdot &&
+             (flat ? a->beta != nullptr : (a->zsel && a->sel && a->zdsel)),
+             "xm_img_dual_fwd: null w/w_dot/gamma/gamma_dot/beta_dot/mean_invstd/dual_red/zsel/sel/pdot/zdsel (beta for stride 2)");
   ImgK k; fill(a, k);
+  if (flat) return flat_launch(2, a, k, stream);
   int rc = 0;
   IMG_DISPATCH(a->g.cin, (rc = launch_fwd<CIN, 1>(a, k, stream)));
   return rc;
@@ -737,10 +736,15 @@ extern "C" int xm_img_dual_fwd(const XmImgArgs* a, void* stream_) {
 extern "C" int xm_img_bwd(const XmImgArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = common_checks(a, "xm_img_bwd")) return rc;
-  XM_REQUIRE(a->w && a->gamma && a->mean_invstd && a->gp && a->zsel && a->sel && a->scratch,
-             "xm_img_bwd: null w/gamma/mean_invstd/gp/zsel/sel/scratch");
+  const bool flat = flat_ok(a->g);
+  XM_REQUIRE(a->w && a->gamma && a->mean_invstd && a->gp && a->scratch && (flat ? a->beta != nullptr : (a->zsel && a->sel)),
+             "xm_img_bwd: null w/gamma/mean_invstd/gp/zsel/sel/scratch (beta for stride 2)");
   XM_REQUIRE((a->out_gamma == nullptr) == (a->out_beta == nullptr), "xm_img_bwd: out_gamma/out_beta must both be given");
   ImgK k; fill(a, k);
+  if (flat) {
+    if (int rc = flat_launch(1, a, k, stream)) return rc;
+    return launch_finalize<1, 0>(a, k, stream);
+  }
   int rc = 0;
   IMG_DISPATCH(a->g.cin, (rc = launch_bwd<CIN, 0>(a, k, stream)));
   return rc;
@@ -749,11 +753,16 @@ extern "C" int xm_img_bwd(const XmImgArgs* a, void* stream_) {
 extern "C" int xm_img_dual_bwd(const XmImgArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = common_checks(a, "xm_img_dual_bwd")) return rc;
+  const bool flat = flat_ok(a->g);
   XM_REQUIRE(a->w && a->w_dot && a->gamma && a->gamma_dot && a->mean_invstd && a->bwd_red && a->dual_red && a->gp &&
-             a->zsel && a->zdsel && a->sel && a->ssum && a->scratch,
+             a->ssum && a->scratch && (flat ? a->beta != nullptr : (a->zsel && a->zdsel && a->sel)),
              "xm_img_dual_bwd: null w/w_dot/gamma/gamma_dot/mean_invstd/bwd_red/dual_red/gp/zsel/zdsel/sel/ssum/scratch");
   XM_REQUIRE((a->out_gamma == nullptr) == (a->out_beta == nullptr), "xm_img_dual_bwd: out_gamma/out_beta must both be given");
   ImgK k; fill(a, k);
+  if (flat) {
+    if (int rc = flat_launch(3, a, k, stream)) return rc;
+    return launch_finalize<1, 1>(a, k, stream);
+  }
   int rc = 0;
   IMG_DISPATCH(a->g.cin, (rc = launch_bwd<CIN, 1>(a, k, stream)));
   return rc;

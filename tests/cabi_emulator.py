@@ -302,8 +302,10 @@ class EmulatedLib:
     # numbers through the Gram-matrix closed forms of exploring_meta_b200/csrc/img_block.cu.
     @staticmethod
     def _img_ok(g):
-        return (1 <= g.cin <= 4 and g.stride == 1 and g.pool == 1 and g.hz % 2 == 0 and g.wz % 2 == 0
-                and g.cout % 32 == 0)
+        pooled = (1 <= g.cin <= 4 and g.stride == 1 and g.pool == 1 and g.hz % 2 == 0 and g.wz % 2 == 0
+                  and g.cout % 32 == 0)
+        flat = g.cin == 1 and g.stride == 2 and g.pool == 0 and g.cout in (32, 64)      # Omniglot image block
+        return pooled or flat
 
     def xm_img_supported(self, ref):
         return 1 if self._img_ok(self._args(ref)) else 0
@@ -324,12 +326,18 @@ class EmulatedLib:
         g = a.g
         x = self._img_x(a)
         W = param(waddr, wstride, g.tasks, (g.cout, g.cin, 3, 3))
-        z = torch.stack([F.conv2d(x[t], W[t], None, stride=1, padding=1) for t in range(g.tasks)])
+        z = torch.stack([F.conv2d(x[t], W[t], None, stride=g.stride, padding=1) for t in range(g.tasks)])
         return z.permute(0, 1, 3, 4, 2).contiguous()                                # NHWC
 
-    def _img_selmask(self, a):
-        """0/1 mask over z positions decoded from the stored winner indices."""
+    def _img_selmask(self, a, z=None):
+        """0/1 mask over z positions decoded from the stored winner indices (no-pool variant: recomputed y > 0)."""
         g = a.g
+        if not g.pool:
+            mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
+            gamma = param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,))
+            beta = param(a.beta, a.gb_task_stride, g.tasks, (g.cout,))
+            y = _bc(gamma) * ((z - _bc(mi[:, 0])) * _bc(mi[:, 1])) + _bc(beta)
+            return (y > 0).to(z.dtype)
         sel = view(a.sel, (g.tasks, g.n, g.hp, g.wp, g.cout), torch.uint8).long()
         m = torch.zeros(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout)
         for d in range(4):
@@ -344,7 +352,7 @@ class EmulatedLib:
         x = self._img_x(a).double()
         out = view(a.gram, (g.tasks, K * K + K), torch.float64)
         for t in range(g.tasks):
-            cols = F.unfold(x[t], 3, padding=1)                  # [n, K, H*W], k = ci*9 + kh*3 + kw
+            cols = F.unfold(x[t], 3, padding=1, stride=g.stride)  # [n, K, positions], k = ci*9 + kh*3 + kw
             X = cols.permute(1, 0, 2).reshape(K, -1)
             out[t, :K * K] = (X @ X.t()).reshape(-1)
             out[t, K * K:] = X.sum(1)
@@ -370,6 +378,9 @@ class EmulatedLib:
         beta = param(a.beta, a.gb_task_stride, g.tasks, (g.cout,))
         xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
         y = _bc(gamma) * xhat + _bc(beta)
+        if not g.pool:
+            view(a.p, y.shape).copy_(F.relu(y))
+            return 0
         yw = y.reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).permute(0, 1, 2, 4, 6, 3, 5).reshape(
             g.tasks, g.n, g.hp, g.wp, g.cout, 4)
         zw = z.reshape(g.tasks, g.n, g.hp, 2, g.wp, 2, g.cout).permute(0, 1, 2, 4, 6, 3, 5).reshape(
@@ -388,7 +399,7 @@ class EmulatedLib:
         mi = view(a.mean_invstd, (g.tasks, 2, g.cout))
         gamma = param(a.gamma, a.gb_task_stride, g.tasks, (g.cout,))
         xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
-        sel = self._img_selmask(a)
+        sel = self._img_selmask(a, z)
         gbn = sel * _up(view(a.gp, (g.tasks, g.n, g.hp, g.wp, g.cout)), g)
         return z, mi, gamma, xhat, sel, gbn
 
@@ -396,7 +407,7 @@ class EmulatedLib:
         g = a.g
         x = self._img_x(a)
         gzn = gz.permute(0, 1, 4, 2, 3).contiguous()
-        return torch.stack([torch.nn.grad.conv2d_weight(x[t], (g.cout, g.cin, 3, 3), gzn[t], stride=1, padding=1)
+        return torch.stack([torch.nn.grad.conv2d_weight(x[t], (g.cout, g.cin, 3, 3), gzn[t], stride=g.stride, padding=1)
                             for t in range(g.tasks)])
 
     def _img_outputs(self, a, gW, ggamma, gbeta):
@@ -445,10 +456,11 @@ class EmulatedLib:
         xhat = (z - _bc(mi[:, 0])) * _bc(mi[:, 1])
         xhd = _bc(mi[:, 1]) * (zd - _bc(dr[:, 0]) - xhat * _bc(dr[:, 1]))
         yd = _bc(gd) * xhat + _bc(gamma) * xhd + _bc(bd)
-        sel = self._img_selmask(a)
+        sel = self._img_selmask(a, z)
         pd = _down(sel * yd, g)
         view(a.pdot, pd.shape).copy_(pd)
-        view(a.zdsel, pd.shape).copy_(_down(sel * zd, g))
+        if g.pool:
+            view(a.zdsel, pd.shape).copy_(_down(sel * zd, g))
         return 0
 
     def xm_img_dual_bwd(self, ref, stream):

@@ -21,6 +21,7 @@ CASES = [
     (pspec.NetSpec(1, 14, 14, 8, 4, 3, False, 'mean'), 1, 1, 0.4, 2),
     (pspec.NetSpec(2, 21, 21, 4, 2, 4, True, 'flatten'), 1, 3, 0.05, 2),   # odd sizes: floor pooling
     (pspec.NetSpec(3, 12, 16, 32, 3, 2, True, 'flatten'), 2, 2, 0.1, 2),   # fused image-block path (xm_img_*)
+    (pspec.NetSpec(1, 14, 14, 32, 4, 3, False, 'mean'), 1, 2, 0.3, 2),     # Omniglot image block (stride 2, no pool)
 ]
 
 
@@ -89,6 +90,8 @@ def test_image_block_path_is_taken(emulated_lib):
     assert names.count('xm_img_dual_fwd') == steps and names.count('xm_img_dual_bwd') == steps
     e8 = eng.MamlEngine(CASES[0][0], tasks, shots, steps, lr, mode='second', device='cpu')
     assert not e8.img and not any(n.startswith('xm_img') for _f, _a, n in e8.prog.calls)
+    eo = eng.MamlEngine(CASES[4][0], 2, 1, 2, 0.3, mode='second', device='cpu')
+    assert eo.img and sum(n == 'xm_img_dual_bwd' for _f, _a, n in eo.prog.calls) == 2
 
 
 @pytest.mark.parametrize('first_order', [False, True])

@@ -193,7 +193,7 @@ def test_image_block_no_base_no_gpdot():
 def test_image_block_rejects_uncovered_geometry():
     lib = _lib.load()
     bad = [XmBlockGeom(2, 3, 3, 32, 21, 21, 21, 21, 10, 10, 1, 1),     # odd map
-           XmBlockGeom(2, 3, 1, 64, 28, 28, 14, 14, 14, 14, 2, 0),     # Omniglot stride-2 block
+           XmBlockGeom(2, 3, 3, 64, 28, 28, 14, 14, 14, 14, 2, 0),     # stride 2 with three input channels
            XmBlockGeom(2, 3, 32, 32, 42, 42, 42, 42, 21, 21, 1, 1),    # not an image layer
            XmBlockGeom(2, 3, 3, 8, 12, 12, 12, 12, 6, 6, 1, 1)]        # narrow
     for g in bad:
@@ -202,3 +202,99 @@ def test_image_block_rejects_uncovered_geometry():
         a.g = g
         assert lib.xm_img_fwd(ctypes.byref(a), None) < 0
         assert b'image-block' in lib.xm_last_error()
+
+
+# ---- Omniglot image block: stride 2, no pool, one input channel (img_flat.cu) --------------------------------------
+FLAT_CASES = [
+    # tasks, n, cout, H, shared weights
+    (2, 5, 64, 28, False),
+    (3, 4, 32, 28, False),
+    (40, 3, 64, 14, True),
+    (2, 100, 64, 28, True),          # config-4 shape per task
+]
+
+
+@pytest.mark.parametrize('case', FLAT_CASES)
+def test_flat_image_block_chain(case):
+    tasks, n, cout, H, shared = case
+    hz = (H + 2 - 3) // 2 + 1
+    g = XmBlockGeom(tasks, n, 1, cout, H, H, hz, hz, hz, hz, 2, 0)
+    K, Pn = 9, 3 * cout + cout * 9
+    lib = _lib.load()
+    assert lib.xm_img_supported(ctypes.byref(g)) == 1
+    torch.manual_seed(7)
+    P = Pair()
+    rows = 2 * n
+    P.add('x', torch.rand(tasks, rows, 1, H, H))
+    wt = 1 if shared else tasks
+    th = torch.zeros(wt, Pn)
+    th[:, :cout] = torch.rand(wt, cout) + 0.1
+    th[:, cout:2 * cout] = torch.randn(wt, cout) * 0.3
+    th[:, 2 * cout:2 * cout + cout * K] = torch.randn(wt, cout * K) * 0.5
+    P.add('theta', th)
+    P.add('v', torch.randn(tasks, Pn) * 0.5)
+    P.out('gram', (tasks, K * K + K), torch.float64)
+    pshape = (tasks, n, hz, hz, cout)
+    P.out('p', pshape).out('pdot', pshape)
+    P.add('gp', torch.randn(*pshape)).add('gpd', torch.randn(*pshape))
+    for name in ('mi', 'cs', 'br', 'dr'):
+        P.out(name, (tasks, 2, cout))
+    P.out('ssum', (tasks, cout, K + 3), torch.float64).out('scratch', (tasks, cout, K + 3), torch.float64)
+    P.out('out', (tasks, Pn))
+    ts = 0 if shared else Pn
+
+    def base(ptr):
+        a = XmImgArgs()
+        a.g, a.eps = g, 1e-5
+        a.row0, a.row_step, a.rows_per_task = 0, 2, rows
+        a.x, a.gram = ptr('x'), ptr('gram')
+        a.gamma, a.beta, a.gb_task_stride = ptr('theta'), ptr('theta', cout), ts
+        a.w, a.w_task_stride = ptr('theta', 2 * cout), ts
+        a.mean_invstd, a.scratch = ptr('mi'), ptr('scratch')
+        return a
+
+    P.run('xm_img_gram', base)
+    P.close('gram', 1e-12, 0)
+
+    def fwd(ptr):
+        a = base(ptr)
+        a.call_stats, a.p = ptr('cs'), ptr('p')
+        return a
+    P.run('xm_img_fwd', fwd)
+    P.close('mi', 2e-6)
+    P.close('cs', 2e-6)
+    P.close('p', 2e-6)
+    alive = (P.cpu['p'] > 0).float().mean().item()
+    assert 0.05 < alive < 0.95
+    _sync(P, 'gram', 'mi')
+
+    def bwd(ptr):
+        a = base(ptr)
+        a.gp, a.bwd_red, a.ssum = ptr('gp'), ptr('br'), ptr('ssum')
+        _outs(a, ptr, cout, K, Pn, base=True)
+        return a
+    P.run('xm_img_bwd', bwd)
+    P.close('br', 5e-6)
+    P.close('ssum', 5e-6)
+    P.close('out', 5e-6)
+    _sync(P, 'br', 'ssum')
+
+    def dfwd(ptr):
+        a = base(ptr)
+        _dual(a, ptr, cout, Pn)
+        a.dual_red, a.pdot = ptr('dr'), ptr('pdot')
+        return a
+    P.run('xm_img_dual_fwd', dfwd)
+    P.close('dr', 5e-6)
+    P.close('pdot', 5e-6)
+    _sync(P, 'dr')
+
+    def dbwd(ptr):
+        a = base(ptr)
+        _dual(a, ptr, cout, Pn)
+        a.gp, a.gpdot, a.bwd_red, a.dual_red, a.ssum = ptr('gp'), ptr('gpd'), ptr('br'), ptr('dr'), ptr('ssum')
+        _outs(a, ptr, cout, K, Pn, base=True)
+        return a
+    P.out('out', (tasks, Pn))
+    P.run('xm_img_dual_bwd', dbwd)
+    P.close('out', 1e-5)
