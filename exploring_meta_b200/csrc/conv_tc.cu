@@ -25,15 +25,18 @@
 // therefore uses FOUR TMEM accumulators -- one per kernel row kh for the hi*hi terms (12 MMAs each) and one for
 // all small correction terms -- which the epilogue sums with round-to-nearest adds.
 //
-// Pipeline (warp-specialised, 1 CTA per SM, 416 threads): warps 0-7 stage tiles (global -> TF32 split -> smem),
-// warps 8-11 drain accumulators (tcgen05.ld -> NHWC store + BatchNorm statistics; warp w reads TMEM lane
-// quarter w%4), one elected lane of warp 12 issues the MMAs.  Two shared-memory stages
-// and two TMEM accumulator sets; mbarrier full/free handshakes; tcgen05.commit signals completion.
+// Pipeline (warp-specialised, 1 CTA per SM, 512 threads): warps 0-6 stage tiles (global -> TF32 split -> smem), one
+// elected lane of warp 7 issues the MMAs, warps 8-11 and 12-15 are two drain groups working on alternate tiles
+// (tcgen05.ld -> kw shift-add -> NHWC store + BatchNorm statistics; warp w reads TMEM lane quarter w%4).  Two
+// shared-memory stages and two TMEM accumulator sets; mbarrier full/free handshakes; tcgen05.commit signals
+// completion.  Measured (XM_TC_TIMING, scripts/gpu_tc_timing.sh): with two drain groups the producers' stores and the
+// MMAs' operand reads share the shared-memory bandwidth and bound a tile at ~2900 cycles (MMA stream alone ~2100).
+// 64-channel and stride-2 layers reuse this kernel through channel-block / full-resolution passes (conv_tc_try).
 #include "tc.cuh"
 
 namespace xm {
 
-constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs  (12 warps = 3 per scheduler: 168 registers each)
+constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs
 constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11, 12-15)
 constexpr int TC_GROUPS = 2;          // drain groups: group g drains tiles g, g + 2, ... (= TMEM set g): a tile's drain is
                                       // latency-bound (TMEM loads, shuffles, exchange) and ~1.5x the MMA time of a tile,
@@ -320,9 +323,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           const long long o_first = odd ? o_pair : o, o_second = odd ? o : o_pair;
           const bool v_first = odd ? v_pair : valid, v_second = odd ? valid : v_pair;
           const int col = half * 16 + (odd ? 4 : 0);
-#ifdef XM_TC_NOSTORE
-          if (acc[0] != 123456.f) continue;
-#endif
           // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector
           // reductions -- no read of the old value, so no load latency in the drain
           if (v_first) {
