@@ -9,8 +9,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 ( timeout 600 python bench.py 2> $OUT/bench.err | tail -1 ) > $OUT/bench.json
 ( timeout 300 python scripts/step_breakdown.py 2>&1 ) > $OUT/breakdown.txt
 if [ -z "$NO_NCU" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
-    python scripts/profile_step.py --inner-steps 1 > $OUT/ncu_launches.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_LAUNCHES:-600} --csv --log-file $OUT/launches.csv \
+    python scripts/profile_step.py --inner-steps ${NCU_INNER_STEPS:-1} > $OUT/ncu_launches.log 2>&1
 fi
 if [ -n "$NCU_FULL" ]; then
 # full-set capture of the kernels named in $NCU_FULL (regex), 2 launches each; the .ncu-rep stays on the box
