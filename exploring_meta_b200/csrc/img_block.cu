@@ -43,14 +43,18 @@ __device__ __forceinline__ const float* image_ptr(const ImgK& p, int task, int i
 template <int CIN>
 __device__ __forceinline__ void issue_band(const ImgK& p, const float* X, int y_first, int rows, float4* dst) {
   const int Wp = p.W + 2, chw = p.H * p.W;
-  for (int i = threadIdx.x; i < rows * Wp; i += blockDim.x) {
-    const int yy = i / Wp, xx = i - yy * Wp;
-    const int y = y_first + yy, x = xx - 1;
-    const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
-    const float* src = in ? X + y * p.W + x : X;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int yy = warp; yy < rows; yy += nwarps) {          // one band row per warp step: no per-element index arithmetic
+    const int y = y_first + yy;
+    const bool rowin = y >= 0 && y < p.H;
+    const float* src = X + (rowin ? y : 0) * p.W - 1;
+    float4* d = dst + yy * Wp;
+    for (int xx = lane; xx < Wp; xx += 32) {
+      const bool in = rowin && xx >= 1 && xx <= p.W;
 #pragma unroll
-    for (int c = 0; c < CIN; ++c)
-      cp_async4(reinterpret_cast<float*>(dst + i) + c, src + (in ? (long long)c * chw : 0), in ? 4 : 0);
+      for (int c = 0; c < CIN; ++c)
+        cp_async4(reinterpret_cast<float*>(d + xx) + c, in ? src + xx + (long long)c * chw : X, in ? 4 : 0);
+    }
   }
   cp_async_commit();
 }
