@@ -62,6 +62,7 @@ struct ConvTcK {
   int R, plane_bytes;                // staged rows per tile, bytes per channel-group plane
   int wmode;                         // 0 forward, 1 data-gradient (transposed weights, flipped taps)
   int stat_mode, accumulate;
+  int ctas_per_task;                 // > 0: CTAs never cross a task boundary (small maps)
   const float* src; const float* w; long long wstride;
   float* out; const float* aux; double* stats;
   // channel blocking (64-channel layers run as 2 x 2 passes over 32-channel blocks): floats per position of the
@@ -73,7 +74,6 @@ struct ConvTcK {
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int task = blockIdx.y;
   constexpr int NPLANES = 8;                      // channel-group planes of the A operand
   constexpr int BFLOATS = 3 * 8 * 96 * 4;         // B[kh][c4][n = kw*32 + cout][4]
   const int plane = p.plane_bytes, set_bytes = NPLANES * plane;   // one hi (or lo) set
@@ -101,6 +101,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
                  "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // ---- CTA -> tiles.  Large maps: persistent grid over the flattened (task, tile) list, CTA c owns tiles
+  // [c*G/n, (c+1)*G/n), i.e. one or two SEGMENTS of consecutive tiles of one task each (the per-task weights are
+  // re-staged at the task boundary) -- every SM gets the same share whatever the task count (32 tasks on 148 SMs: 4 CTAs
+  // per task leave 20 SMs idle).  Small maps (few tiles per CTA): whole CTAs per task (p.ctas_per_task > 0).
+  int g_lo, g_hi;
+  if (p.ctas_per_task > 0) {
+    const int t = blockIdx.x / p.ctas_per_task, c = blockIdx.x - t * p.ctas_per_task;
+    g_lo = t * p.tiles_per_task + (int)((long long)p.tiles_per_task * c / p.ctas_per_task);
+    g_hi = t * p.tiles_per_task + (int)((long long)p.tiles_per_task * (c + 1) / p.ctas_per_task);
+  } else {
+    const long long G = (long long)p.tasks * p.tiles_per_task;
+    g_lo = (int)(G * blockIdx.x / gridDim.x);
+    g_hi = (int)(G * (blockIdx.x + 1) / gridDim.x);
+  }
+  uint32_t tmem_base = 0;
+  for (int gt = g_lo, seg = 0; gt < g_hi; ++seg) {
+  const int task = gt / p.tiles_per_task, tile0 = gt - task * p.tiles_per_task;
+  const int ntiles = min(g_hi - gt, p.tiles_per_task - tile0);   // my tiles of this task: tile0 .. tile0 + ntiles - 1
+  gt += ntiles;
+  if (seg > 0) {
+    // every role is done with the previous segment (the drainers waited for its last accumulators, which also
+    // completes every MMA that read the weights / stages): barriers restart from phase 0
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+        mbar_init(bar_sfree + 8 * s, 1);
+        mbar_init(bar_tfull + 8 * s, 1);
+        mbar_init(bar_tfree + 8 * s, TC_DRAINERS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   // ---- resident weights, split into TF32 hi / lo: B[kh][k/4][n = kw*32 + out channel][k%4] ---------------
   {
     const float* W = p.w + (long long)task * p.wstride;       // [co][ci][3][3]
@@ -121,10 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int ntiles = (p.tiles_per_task - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // my tiles
-  const int HpWp = p.Hp * p.Wp;
+  tmem_base = *tmem_slot;
 
   if (warp < 7) {
     // ========================================= producers =============================================
@@ -135,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     const int c8 = tid & 3, jrow = tid >> 2;                   // channel octet (two planes), first row (0..PR-1)
     const float* S = p.src + (long long)task * p.n * p.H * p.W * p.src_cs + p.src_co + c8 * 8;
     auto issue_loads = [&](int it, float4 (&v)[8]) {
-      const int qbase = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE - p.Wp - 1 + jrow;
+      const int qbase = (tile0 + it) * TC_TILE - p.Wp - 1 + jrow;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {                              // 4 independent rows: no carried state
         const int j = jrow + PR * u;
@@ -220,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t0 = clock64();
 #endif
-      const int q = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TILE + row;
+      const int q = (tile0 + it) * TC_TILE + row;
       const int px = row < TC_TILE ? pos_to_pixel(p.pm, q) : -1;
       const bool valid = px >= 0;
       const long long o = ((long long)task * p.n * p.H * p.W + (valid ? px : 0)) * p.out_cs + p.out_co;
@@ -445,6 +476,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #endif
   }
 
+  }   // segments
+
   tc_fence_before();
   __syncthreads();
   if (warp == 7) {
@@ -565,10 +598,18 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   p.wmode = a->mode == XM_CONV_FWD ? 0 : 1;
   p.out = a->out; p.aux = a->aux; p.stats = a->stats;
   p.src_cs = p.out_cs = p.w_cin = g.cout;
-  int per_task = num_sms() / g.tasks;
-  if (per_task < 1) per_task = 1;
-  if (per_task > p.tiles_per_task) per_task = p.tiles_per_task;
-  dim3 grid(per_task, g.tasks);
+  // persistent grid when a CTA gets enough tiles to amortise re-staging the weights at a task boundary
+  const long long total_tiles = (long long)g.tasks * p.tiles_per_task;
+  int ctas = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  p.ctas_per_task = 0;
+  if (total_tiles / ctas < 24 || g.tasks >= num_sms()) {
+    int per_task = num_sms() / g.tasks;
+    if (per_task < 1) per_task = 1;
+    if (per_task > p.tiles_per_task) per_task = p.tiles_per_task;
+    p.ctas_per_task = per_task;
+    ctas = per_task * g.tasks;
+  }
+  dim3 grid(ctas);
   static bool attr_set = false;
   if (!attr_set) {
     XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
