@@ -246,10 +246,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION / WARN) to stdout when the communicator is created: point
+        # fd 1 at stderr until then so that stdout carries exactly the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     lib = _lib.load()
     lib.xm_set_precision(0 if args.fast_tf32 else 1)
 
