@@ -368,7 +368,7 @@ def run_ours(args):
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'tasks_per_gpu': args.tasks, 'global_meta_batch': global_tasks,
                    'inner_steps': T, 'inner_lr': INNER_LR, 'ways': WAYS, 'shots': SHOTS,
-                   'parallelism': 'tasks sharded over %d GPU(s), one fp32 allreduce of %d floats per step' % (world, e.P + 2),
+                   'parallelism': 'tasks sharded over %d GPU(s), one fp32 allreduce of %d floats per step' % (world, tr.flat.numel()),
                    'l2_policy': 'inputs (135.5 MB/step) and activations (several GB/step) exceed the 126 MB L2; no explicit flush',
                    'cuda_graph': bool(tr.use_graph)},
         'e2e': {'value': e2e, 'unit': 'tasks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

@@ -18,15 +18,15 @@ ADAM_EPS = 1e-8
 
 
 class _TrainerBase:
-    def _init_common(self, device, outer_lr, total_params, use_graph):
+    def _init_common(self, device, outer_lr, total_params, use_graph, extra=0):
         self.device = torch.device(device)
         self.lib = _lib.load()
         self.outer_lr = float(outer_lr)
         self.iteration = 0
         self.use_graph = bool(use_graph)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        # flat fp32 buffer that is all-reduced: [grad (total_params) ; loss sum ; correct count]
-        self.flat = torch.zeros(total_params + 2, dtype=torch.float32, device=self.device)
+        # flat fp32 buffer that is all-reduced: [grad (total_params) ; loss sum ; correct count ; BN EMA partials (extra)]
+        self.flat = torch.zeros(total_params + 2 + extra, dtype=torch.float32, device=self.device)
         self.m = torch.zeros(total_params, dtype=torch.float32, device=self.device)
         self.v = torch.zeros(total_params, dtype=torch.float32, device=self.device)
 
@@ -88,7 +88,11 @@ class MamlTrainer(_TrainerBase):
         self.engine = MamlEngine(spec, tasks, shots, steps, inner_lr,
                                  mode='first' if first_order else 'second', device=device)
         self.spec, self.tasks = spec, int(tasks)
-        self._init_common(device, outer_lr, self.engine.P, use_graph)
+        # sharded runs carry the BatchNorm running-statistics side effect in the same allreduce: per layer the rank's
+        # composed EMA contribution {mean[C], var[C]}
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._init_common(device, outer_lr, self.engine.P, use_graph,
+                          extra=2 * spec.layers * spec.hidden if world > 1 else 0)
         self.theta = self.engine.theta
         self.running_mean = [torch.zeros(spec.hidden, device=self.device) for _ in range(spec.layers)]
         self.running_var = [torch.ones(spec.hidden, device=self.device) for _ in range(spec.layers)]
@@ -120,8 +124,38 @@ class MamlTrainer(_TrainerBase):
         self.flat[P + 1] = e.correct.sum()
         if track_running_stats and self.world == 1:
             self.num_batches_tracked += e.update_running_stats(self.running_mean, self.running_var)
+        elif track_running_stats:
+            self._stage_running_stats()
         self._reduce_and_step(self.theta, self.tasks * self.world)
+        if track_running_stats and self.world > 1:
+            self._apply_running_stats()
         return e.loss, e.correct
+
+    # The reference's shared BN buffers see one EMA update r <- (1-m) r + m s per forward call, task after task
+    # (vision/maml_vision.py:102-112 through learn2learn's clones).  The recurrence is linear: over the N calls of the
+    # global meta-batch r_N = (1-m)^N r_0 + sum_k m (1-m)^(N-k) s_k, and the sum splits by rank: rank q contributes the
+    # EMA of ITS calls started from zero, damped by (1-m)^(calls of the ranks after it).  Those contributions ride in
+    # the meta-gradient allreduce; every rank then applies the same closed form.
+    def _stage_running_stats(self):
+        e, L, C = self.engine, self.spec.layers, self.spec.hidden
+        rank = dist.get_rank()
+        calls = self.tasks * (e.steps + 1)                     # forward calls of one rank per layer
+        tail = self.flat[e.P + 2:].view(L, 2, C)
+        tail.zero_()
+        e.update_running_stats([tail[l, 0] for l in range(L)], [tail[l, 1] for l in range(L)])
+        from .engine import BN_MOMENTUM
+        tail.mul_((1.0 - BN_MOMENTUM) ** (calls * (self.world - 1 - rank)))
+
+    def _apply_running_stats(self):
+        e, L, C = self.engine, self.spec.layers, self.spec.hidden
+        from .engine import BN_MOMENTUM
+        calls = self.tasks * (e.steps + 1) * self.world
+        decay = (1.0 - BN_MOMENTUM) ** calls
+        tail = self.flat[e.P + 2:].view(L, 2, C)
+        for l in range(L):
+            self.running_mean[l].mul_(decay).add_(tail[l, 0])
+            self.running_var[l].mul_(decay).add_(tail[l, 1])
+        self.num_batches_tracked += calls
 
     def metrics(self):
         P, n = self.engine.P, self.tasks * self.world

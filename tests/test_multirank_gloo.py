@@ -49,7 +49,12 @@ def _one_step(kind, tasks, lo, hi, steps=2):
     for _ in range(steps):
         tr.meta_step(X[lo:hi], Y[lo:hi])
     loss, acc = tr.metrics()
-    return theta.clone(), float(loss), float(acc)
+    if kind == 'maml':       # BatchNorm running statistics: the sharded run composes the ranks' EMA contributions
+        stats = torch.cat([torch.cat(tr.running_mean), torch.cat(tr.running_var),
+                           torch.tensor([float(tr.num_batches_tracked)])])
+    else:
+        stats = torch.zeros(1)
+    return theta.clone(), float(loss), float(acc), stats
 
 
 def _worker(rank, world, port, kind, tasks, out):
@@ -57,8 +62,8 @@ def _worker(rank, world, port, kind, tasks, out):
     _install_emulator()
     dist.init_process_group('gloo', rank=rank, world_size=world)
     per = tasks // world
-    theta, loss, acc = _one_step(kind, tasks, rank * per, (rank + 1) * per)
-    out[rank] = (theta, loss, acc)
+    theta, loss, acc, stats = _one_step(kind, tasks, rank * per, (rank + 1) * per)
+    out[rank] = (theta, loss, acc, stats)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -81,12 +86,15 @@ def test_two_ranks_equal_one_process(kind):
     from exploring_meta_b200 import _lib, engine
     saved = (_lib._lib, engine._require_cuda)
     try:
-        ref_theta, ref_loss, ref_acc = _one_step(kind, tasks, 0, tasks)
+        ref_theta, ref_loss, ref_acc, ref_stats = _one_step(kind, tasks, 0, tasks)
     finally:
         _lib._lib = None
         import importlib
         importlib.reload(engine)
-    (t0, l0, a0), (t1, l1, a1) = results[0], results[1]
+    (t0, l0, a0, s0), (t1, l1, a1, s1) = results[0], results[1]
+    # running statistics after two sharded iterations == the single-process sequence of per-call EMA updates
+    assert torch.equal(s0, s1)
+    assert torch.allclose(s0, ref_stats, rtol=1e-5, atol=1e-6)
     assert torch.equal(t0, t1)                                    # replicated Adam: bit-identical across ranks
     assert (t0 - ref_theta).abs().max() <= 1e-6 * ref_theta.abs().max()   # fp32 reassociation of the task sum only
     assert l0 == pytest.approx(ref_loss, rel=1e-5) and l1 == pytest.approx(ref_loss, rel=1e-5)
