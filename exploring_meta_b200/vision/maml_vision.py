@@ -85,10 +85,28 @@ def compose_bn_side_effects(model, engines, device):
     E, T1, L, B, _two, C = stacked.shape
     seq = stacked.permute(2, 3, 0, 1, 4, 5).contiguous()              # [L, B, E, T+1, 2, C]
     stream = torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0
-    for l, bn in enumerate(bns):
-        _lib.check(lib.xm_bn_ema(_p(bn.running_mean), _p(bn.running_var), _p(seq[l]), B * E * T1, 2 * C, 1, 0, C,
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    calls = B * E * T1
+    if world == 1:
+        for l, bn in enumerate(bns):
+            _lib.check(lib.xm_bn_ema(_p(bn.running_mean), _p(bn.running_var), _p(seq[l]), calls, 2 * C, 1, 0, C,
+                                     BN_MOMENTUM, stream), 'xm_bn_ema')
+            bn.num_batches_tracked += calls
+        return
+    # Sharded meta-batch: the EMA over forward calls is linear, so this rank contributes the EMA of its own calls
+    # started from zero, damped by (1-m)^(calls of the ranks after it); one small allreduce, then every rank applies
+    # r <- (1-m)^N r + sum (same closed form as trainer.MamlTrainer).
+    part = torch.zeros(len(bns), 2, C, dtype=torch.float32, device=device)
+    for l in range(len(bns)):
+        _lib.check(lib.xm_bn_ema(_p(part[l, 0]), _p(part[l, 1]), _p(seq[l]), calls, 2 * C, 1, 0, C,
                                  BN_MOMENTUM, stream), 'xm_bn_ema')
-        bn.num_batches_tracked += B * E * T1
+    part.mul_((1.0 - BN_MOMENTUM) ** (calls * (world - 1 - dist.get_rank())))
+    dist.all_reduce(part)
+    decay = (1.0 - BN_MOMENTUM) ** (calls * world)
+    for l, bn in enumerate(bns):
+        bn.running_mean.mul_(decay).add_(part[l, 0])
+        bn.running_var.mul_(decay).add_(part[l, 1])
+        bn.num_batches_tracked += calls * world
 
 
 class MamlVision(Experiment):
