@@ -119,11 +119,13 @@ class _EngineBase:
             self.img_scratch = self._f64(int(self.lib.xm_img_scratch_bytes(ctypes.byref(g))) // 8)
             self._gram_words = self.tasks * (K * K + K)
 
-    def _img_state(self, n, dual=False):
-        """Side buffers of one image-block call: winner values / positions and the sparse sums."""
-        st = {'zsel': self._f32(*self.pshape(0, n)),
-              'sel': torch.empty(self.pshape(0, n), dtype=torch.uint8, device=self.device),
-              'ssum': self._f64(self.tasks, self.C, 9 * self.spec.in_c + 3)}
+    def _img_state(self, n):
+        """Side buffers of one image-block call: winner values / positions (pooled variant only: the stride-2
+        variant recomputes everything from the image) and the sparse sums of the backward."""
+        st = {'ssum': self._f64(self.tasks, self.C, 9 * self.spec.in_c + 3), 'zsel': None, 'sel': None}
+        if self.spec.pool:
+            st['zsel'] = self._f32(*self.pshape(0, n))
+            st['sel'] = torch.empty(self.pshape(0, n), dtype=torch.uint8, device=self.device)
         return st
 
     def _img_args(self, n, img, gram, theta, tstride):
@@ -310,7 +312,7 @@ class MamlEngine(_EngineBase):
         self.BR = [[self._f32(B, 2, C) for l in range(L)] for _ in range(keep)]
         # temporaries: query pass (phase 2) and dual sweep (phase 3) share them
         self.tZ = [(self.gram_qry, self._img_state(S)) if l < l0 else self._f32(*self.zshape(l, S)) for l in range(L)]
-        self.tZD = self._f32(*self.pshape(0, S)) if (self.img and mode == 'second') else None   # zdot at the winners
+        self.tZD = self._f32(*self.pshape(0, S)) if (self.img and spec.pool and mode == 'second') else None   # zdot at the winners
         self.tP = [self._f32(*self.pshape(l, S)) for l in range(L)]
         self.tGP = [self._f32(*self.pshape(l, S)) for l in range(L)]
         self.tMI = [self._f32(B, 2, C) for l in range(L)]
