@@ -52,3 +52,28 @@ def get_tasks(dataset, ways, shots, seed=0):
     datasets that need a download): three independent synthetic task streams ``(train, valid, test)``."""
     shape = (1, 28, 28) if dataset == 'omni' else (3, 84, 84)
     return tuple(SyntheticTasks(ways, shots, shape, seed=seed + 1_000_003 * k) for k in range(3))
+
+
+def make_replays(tasks, episodes=20, horizon=100, seed=0, dtype=torch.float32):
+    """Synthetic Particles2D-style rollouts for the MAML-TRPO policy path: per task a
+    support and a query replay of ``episodes * horizon`` transitions -- states ~ 0.3 N(0, 1) random walks, actions
+    ~ 0.1 N(0, 1), reward = -||s' - goal|| with goal ~ U[-0.5, 0.5]^2, ``done`` at the end of every episode.
+    Returns a list (tasks) of [support, query] dicts with keys states / actions / rewards / dones / next_states."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(int(seed))
+    n = episodes * horizon
+    out = []
+    for _ in range(tasks):
+        goal = torch.rand(2, generator=gen, dtype=torch.float32) - 0.5
+        pair = []
+        for _k in range(2):
+            s = 0.3 * torch.randn(n, 2, generator=gen, dtype=torch.float32)   # fp32 draws whatever the default dtype
+            a = 0.1 * torch.randn(n, 2, generator=gen, dtype=torch.float32)
+            ns = s + a
+            r = -(ns - goal).norm(dim=1, keepdim=True)
+            d = torch.zeros(n, 1, dtype=torch.float32)
+            d[horizon - 1::horizon] = 1.0
+            pair.append({'states': s.to(dtype), 'actions': a.to(dtype), 'rewards': r.to(dtype), 'dones': d.to(dtype),
+                         'next_states': ns.to(dtype)})
+        out.append(pair)
+    return out
