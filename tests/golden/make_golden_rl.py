@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generates tests/golden/rl_trpo_small.npz from the REFERENCE'S OWN FILES (build container only):
+"""Generates tests/golden/rl/rl_trpo_small.npz from the REFERENCE'S OWN FILES (build container only):
 
     python tests/golden/make_golden_rl.py            # needs /root/reference
 
@@ -64,7 +64,7 @@ def main():
     print('restatement == reference files: old_loss %.12f  old_kl %.3e  line-search step %d' % (
         diag['old_loss'], diag['old_kl'], diag['ls_step']))
     flat = lambda ps: torch.cat([p.reshape(-1) for p in ps]).numpy()                                   # noqa: E731
-    np.savez_compressed(os.path.join(HERE, 'rl_trpo_small.npz'), theta0=flat(theta0), theta1=flat(theta1),
+    np.savez_compressed(os.path.join(HERE, 'rl', 'rl_trpo_small.npz'), theta0=flat(theta0), theta1=flat(theta1),
                         old_params=np.stack([flat(p) for p in old_params]), old_loss=float(old_loss),
                         old_kl=float(old_kl), grad=diag['grad'].numpy(), step=diag['step'].numpy(),
                         ls_step=diag['ls_step'], tasks=TASKS, episodes=EPISODES, horizon=HORIZON, seed=SEED)
