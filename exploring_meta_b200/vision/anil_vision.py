@@ -122,10 +122,26 @@ class AnilVision(Experiment):
             seq = torch.stack([trainer.engine.call_stats, valid.call_stats]).permute(1, 2, 0, 3, 4).contiguous()
             stream = torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0
             C = spec.hidden
-            for l, bn in enumerate(bns):                                  # seq: [L, B, 2 engines, 2, C]
-                _lib.check(lib.xm_bn_ema(_p(bn.running_mean), _p(bn.running_var), _p(seq[l]), 2 * B, 2 * C, 1, 0, C,
+            world = dist.get_world_size() if dist.is_initialized() else 1
+            if world == 1:
+                for l, bn in enumerate(bns):                              # seq: [L, B, 2 engines, 2, C]
+                    _lib.check(lib.xm_bn_ema(_p(bn.running_mean), _p(bn.running_var), _p(seq[l]), 2 * B, 2 * C, 1, 0, C,
+                                             BN_MOMENTUM, stream), 'xm_bn_ema')
+                    bn.num_batches_tracked += 2 * B
+                return
+            # sharded meta-batch: EMA partials of this rank's calls, damped by the calls of the later ranks, summed
+            # over ranks; then r <- (1-m)^N r + sum  (same closed form as maml_vision.compose_bn_side_effects)
+            part = torch.zeros(len(bns), 2, C, dtype=torch.float32, device=device)
+            for l in range(len(bns)):
+                _lib.check(lib.xm_bn_ema(_p(part[l, 0]), _p(part[l, 1]), _p(seq[l]), 2 * B, 2 * C, 1, 0, C,
                                          BN_MOMENTUM, stream), 'xm_bn_ema')
-                bn.num_batches_tracked += 2 * B
+            part.mul_((1.0 - BN_MOMENTUM) ** (2 * B * (world - 1 - dist.get_rank())))
+            dist.all_reduce(part)
+            decay = (1.0 - BN_MOMENTUM) ** (2 * B * world)
+            for l, bn in enumerate(bns):
+                bn.running_mean.mul_(decay).add_(part[l, 0])
+                bn.running_var.mul_(decay).add_(part[l, 1])
+                bn.num_batches_tracked += 2 * B * world
 
         iteration = 0
         t0 = time.time()
