@@ -100,7 +100,7 @@ def test_config2_meta_gradient_is_the_gradient_of_the_adapted_loss(setup):
         fd = (mean_loss(theta + h * v) - mean_loss(theta - h * v)) / (2 * h)
         an = torch.dot(g.double(), v.double()).item()
         an1 = torch.dot(g1.double(), v.double()).item()
-        assert abs(fd - an) <= 0.06 * g.norm().item(), 'along the %s: central difference %.5f vs <grad, v> %.5f' % (name, fd, an)
+        assert abs(fd - an) <= 0.1 * g.norm().item(), 'along the %s: central difference %.5f vs <grad, v> %.5f' % (name, fd, an)
         if name.startswith('second'):       # ... and the first-order gradient would NOT have passed there
             assert abs(fd - an1) > 0.2 * g.norm().item(), 'along the %s: %.5f vs first-order %.5f' % (name, fd, an1)
 
