@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generates tests/golden/*.npz from the REFERENCE'S OWN FILES (build container only).
 
-    python tests/golden/make_golden.py            # needs /root/reference
+    python tests/golden/make_golden.py [case ...] # needs /root/reference; no names = every case
 
 For every case below the train half of one outer iteration (vision/maml_vision.py:95-112 or
 vision/anil_vision.py:109-122) is replayed through oracle/reference_run.py -- the reference's unmodified
@@ -43,6 +43,13 @@ CASES = {
     # configs[2]: ANIL Mini-ImageNet 5-way 5-shot, 64-filter body, head-only adaptation, 1 step
     'anil_min_5w5s_t1': ('anil', 'min', 5, 5, 1, 0.5, 2, 6),
     'anil_omni_5w1s_t2': ('anil', 'omni', 5, 1, 2, 0.5, 3, 7),
+    # configs[1] EXACTLY (5-way 5-shot => S = 25 support rows, T = 5 inner steps) at the calm inner lr, 2 tasks:
+    # the tight-tolerance twin of the chaotic headline case.  Data seed 13 is chosen because the reference's own
+    # fp32 run stays on the fp64 run's ReLU / max-pool decisions there (e_ref 2.6e-5); at S = 25 most seeds do not
+    # even at this lr (seeds 2, 12, 15, 16: e_ref 0.8e-2 .. 2.3e-2 from a flipped decision, seed 14: 3.8e-4)
+    'maml_min_5w5s_t5_calm': ('maml', 'min', 5, 5, 5, 0.001, 2, 13),
+    # configs[0] at its full meta-batch: 32 tasks
+    'maml_omni_5w1s_t1_b32': ('maml', 'omni', 5, 1, 1, 0.5, 32, 8),
 }
 
 IN_SHAPE = {'omni': (1, 28, 28), 'min': (3, 84, 84)}
@@ -71,7 +78,9 @@ def run_reference(algo, kind, ways, shots, steps, lr, X, Y, dtype):
 
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
-    for name, (algo, kind, ways, shots, steps, lr, tasks, seed) in CASES.items():
+    wanted = sys.argv[1:] or list(CASES)
+    for name in wanted:
+        algo, kind, ways, shots, steps, lr, tasks, seed = CASES[name]
         X, Y = make_tasks(tasks, ways, shots, IN_SHAPE[kind], seed=seed)
         r64 = run_reference(algo, kind, ways, shots, steps, lr, X, Y, torch.float64)
         r32 = run_reference(algo, kind, ways, shots, steps, lr, X, Y, torch.float32)
