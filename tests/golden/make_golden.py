@@ -44,10 +44,11 @@ CASES = {
     'anil_min_5w5s_t1': ('anil', 'min', 5, 5, 1, 0.5, 2, 6),
     'anil_omni_5w1s_t2': ('anil', 'omni', 5, 1, 2, 0.5, 3, 7),
     # configs[1] EXACTLY (5-way 5-shot => S = 25 support rows, T = 5 inner steps) at the calm inner lr, 2 tasks:
-    # the tight-tolerance twin of the chaotic headline case.  Data seed 13 is chosen because the reference's own
-    # fp32 run stays on the fp64 run's ReLU / max-pool decisions there (e_ref 2.6e-5); at S = 25 most seeds do not
-    # even at this lr (seeds 2, 12, 15, 16: e_ref 0.8e-2 .. 2.3e-2 from a flipped decision, seed 14: 3.8e-4)
-    'maml_min_5w5s_t5_calm': ('maml', 'min', 5, 5, 5, 0.001, 2, 13),
+    # the tight-tolerance twin of the chaotic headline case.  Even at this lr the S = 25, T = 5 shape is rarely calm:
+    # over data seeds 100..115 the reference's own fp32 run leaves the fp64 run's ReLU / max-pool decisions in 11 of
+    # 16 seeds (e_ref 1e-4 .. 4e-2) and the CUDA path in 10 of 16, often on the same decision
+    # (scripts/diag_flip_rate.py, profiles/r02_flip_rate.txt).  Seed 108 is one where both stay on them.
+    'maml_min_5w5s_t5_calm': ('maml', 'min', 5, 5, 5, 0.001, 1, 108),
     # configs[0] at its full meta-batch: 32 tasks
     'maml_omni_5w1s_t1_b32': ('maml', 'omni', 5, 1, 1, 0.5, 32, 8),
 }

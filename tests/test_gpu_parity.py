@@ -75,6 +75,35 @@ def test_miniimagenet_5w5s_five_steps_config2_shape_calm_lr():
     print('cfg-2 shape, calm lr: e_new %.3e e_ref %.3e' % (e_new, e_ref))
 
 
+def test_config2_shape_decision_flips_no_more_frequent_than_reference_fp32():
+    """At S = 25, T = 5 a single task evaluates 5 x 4 layers x up to 1.4 M ReLU / max-pool decisions; a pre-activation
+    pair that ties to fp32 rounding sends the gradient to a different winner and moves the meta-gradient by 1e-4..4e-2
+    -- in the reference's OWN fp32 run as often as in ours (profiles/r02_flip_rate.txt: 11 vs 10 of 16 seeds).  Per
+    seed the tolerance contract therefore cannot be tight; what must hold: the query loss and the correct count agree
+    with fp64 on every seed, seeds where neither run flips agree to rounding, and our flip count does not exceed the
+    reference's by more than one."""
+    spec, ospec = pspec.miniimagenet_spec(5), _ospec(pspec.miniimagenet_spec(5))
+    params = mo.init_params(ospec, seed=42)
+    mask = ~mo.conv_bias_mask(ospec)
+    e = eng.MamlEngine(spec, 1, 5, 5, 0.001, mode='second', device='cuda')
+    flips_ref = flips_new = 0
+    for seed in range(100, 108):
+        X, Y = make_tasks(1, 5, 5, (3, 84, 84), seed=seed)
+        r64 = mo.meta_iteration([p.double() for p in params], X.double(), Y, ospec, 5, 0.001)
+        r32 = mo.meta_iteration(params, X, Y, ospec, 5, 0.001)
+        e.run(X.cuda(), Y.cuda(), mo.flatten(params).cuda())
+        g64 = mo.flatten(r64['grad'])[mask]
+        e_ref, e_new = mo.rel_l2(mo.flatten(r32['grad'])[mask], g64), mo.rel_l2(e.grad.cpu()[mask], g64)
+        assert torch.allclose(e.loss.cpu().double(), r64['loss'], rtol=1e-4, atol=1e-5)
+        assert e.correct.cpu().tolist() == r64['correct'].tolist()
+        flips_ref += e_ref > 1e-4
+        flips_new += e_new > 1e-4
+        if e_ref <= 1e-4 and e_new <= 1e-4:
+            assert e_new <= max(2e-5, 4 * e_ref)
+        assert e_new <= 0.1                      # a flip, not a wrong kernel: the largest observed is 3.6e-2
+    assert flips_new <= flips_ref + 1, (flips_new, flips_ref)
+
+
 def test_omniglot_20w5s_config4_four_tasks():
     _check_maml(pspec.omniglot_spec(20), 5, 1, 0.5, 4, seed=21)
 
