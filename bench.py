@@ -1,12 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- meta-train tasks/sec of the MAML hot path (BASELINE.json configs[1]):
-MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, meta-batch 32 per GPU.
+"""bench.py -- meta-train tasks/sec of the MAML / ANIL hot path.  Default = BASELINE.json configs[1]:
+MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, GLOBAL meta-batch 32.
 
   python bench.py [--gpus N --steps K --warmup W]          our arm (N>1: launched under torchrun)
   python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+  python bench.py --config 4 ...                           MAML Omniglot 20-way 5-shot, global meta-batch 256
+                                                           (configs 1 and 3 likewise: parity cases, not the headline)
 
-One "step" = one meta-iteration over one synthetic meta-batch: adapt T steps on the support rows of every
-task, query loss, second-order meta-gradient, (allreduce), grad/B, Adam.  Prints ONE JSON line (rank 0).
+Scaling is STRONG by default: the named global meta-batch is sharded over the N ranks (32 -> 32/N tasks per GPU), as
+north_star states the target; ``--scaling weak`` keeps the named batch PER GPU.  With N > 1 the strong run also times
+the weak variant and reports it under "weak_scaling".
+
+One "step" = one meta-iteration over one synthetic meta-batch: adapt T steps on the support rows of every task, query
+loss, second-order meta-gradient, sum over ranks (NVLink peer memory, inside the Adam kernel), grad/B, Adam, BN
+running-statistics update.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -19,10 +26,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WAYS, SHOTS, STEPS, INNER_LR, OUTER_LR, TASKS = 5, 5, 5, 0.5, 0.003, 32
-METRIC = 'meta-train tasks/sec (MAML MiniImageNet 5w5s)'
-WORKLOAD = ('MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, '
-            'meta-batch 32 per GPU (synthetic 84x84x3)')
+OUTER_LR = 0.003
+# BASELINE.json configs (1-based).  flops: SURVEY App. C (spec.flops_per_train_task)
+CONFIGS = {
+    1: dict(algo='maml', kind='omni', ways=5, shots=1, steps=1, inner_lr=0.5, batch=32,
+            metric='meta-train tasks/sec (MAML Omniglot 5w1s)',
+            workload='MAML Omniglot 5-way 1-shot, 4-conv 64-filter CNN, 1 inner step, second-order, meta-batch 32 '
+                     '(synthetic 28x28x1)'),
+    2: dict(algo='maml', kind='min', ways=5, shots=5, steps=5, inner_lr=0.5, batch=32,
+            metric='meta-train tasks/sec (MAML MiniImageNet 5w5s)',
+            workload='MAML Mini-ImageNet 5-way 5-shot, 4-conv 32-filter CNN, 5 inner steps, second-order, '
+                     'meta-batch 32 (synthetic 84x84x3)'),
+    3: dict(algo='anil', kind='min', ways=5, shots=5, steps=1, inner_lr=0.5, batch=32,
+            metric='meta-train tasks/sec (ANIL MiniImageNet 5w5s)',
+            workload='ANIL Mini-ImageNet 5-way 5-shot, 64-filter body forward once + head-only adaptation, '
+                     'meta-batch 32 (synthetic 84x84x3)'),
+    4: dict(algo='maml', kind='omni', ways=20, shots=5, steps=1, inner_lr=0.5, batch=256,
+            metric='meta-train tasks/sec (MAML Omniglot 20w5s)',
+            workload='MAML Omniglot 20-way 5-shot, 4-conv 64-filter CNN, 1 inner step, second-order, meta-batch 256 '
+                     '(synthetic 28x28x1)'),
+}
+IN_SHAPE = {'omni': (1, 28, 28), 'min': (3, 84, 84)}
 
 
 def parse():
@@ -31,12 +55,23 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--tasks', type=int, default=TASKS, help='meta-batch per GPU (default: the named config)')
-    ap.add_argument('--inner-steps', type=int, default=STEPS)
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--tasks', type=int, default=0, help='tasks per GPU (default: from --config and --scaling)')
+    ap.add_argument('--inner-steps', type=int, default=0, help='override the config\'s inner steps')
     ap.add_argument('--fast-tf32', action='store_true', help='single-pass TF32 contractions (not parity-grade)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-breakdown', action='store_true')
+    ap.add_argument('--no-weak', action='store_true', help='skip the extra weak-scaling leg of a strong N>1 run')
     return ap.parse_args()
+
+
+def config_dict(cfg, args, world, tasks_per_gpu, scaling):
+    """The ``config`` object of the JSON line -- identical for our arm and the reference arm."""
+    T = args.inner_steps or cfg['steps']
+    return {'workload': cfg['workload'], 'baseline_config': args.config, 'global_meta_batch': tasks_per_gpu * world,
+            'inner_steps': T, 'inner_lr': cfg['inner_lr'], 'ways': cfg['ways'], 'shots': cfg['shots'],
+            'order': 'second' if cfg['algo'] == 'maml' else 'anil (second-order head adaptation)'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -99,24 +134,31 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(tasks, reps, inner_steps):
-    """The reference's CPU path (oracle port: reference model + fast_adapt semantics + learn2learn
-    restatement, fp32, torch intra-op threads = all host cores), train tasks only incl. second-order
-    backward; returns tasks/s over `reps` timed repetitions of a `tasks`-task sample after one warm-up task."""
+def cpu_reference_rate(cfg, tasks, reps, inner_steps, threads=None):
+    """The reference's CPU path (oracle port: reference model + fast_adapt semantics + learn2learn restatement, fp32,
+    torch intra-op threads = all host cores unless given), train tasks only incl. the second-order backward, grad/B
+    and the Adam step; returns tasks/s over ``reps`` timed repetitions of a ``tasks``-task sample after a 1-task
+    warm-up."""
     import torch
     from oracle import maml_oracle as mo
     from exploring_meta_b200.synthetic import make_tasks
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ospec = mo.miniimagenet_spec(WAYS)
-    params = mo.init_params(ospec, seed=42)
-    X, Y = make_tasks(tasks, WAYS, SHOTS, (3, 84, 84), seed=0)
-    mo.meta_iteration(params, X[:1], Y[:1], ospec, inner_steps, INNER_LR)     # warm-up
+    ways, shots = cfg['ways'], cfg['shots']
+    head = None
+    if cfg['algo'] == 'anil':
+        ospec = mo.NetSpec(3, 84, 84, 64, ways, 4, True, 'flatten')
+        params, head = mo.init_anil_params(ospec, seed=42)
+    else:
+        ospec = mo.omniglot_spec(ways) if cfg['kind'] == 'omni' else mo.miniimagenet_spec(ways)
+        params = mo.init_params(ospec, seed=42)
+    X, Y = make_tasks(tasks, ways, shots, IN_SHAPE[cfg['kind']], seed=0)
+    mo.meta_iteration(params, X[:1], Y[:1], ospec, inner_steps, cfg['inner_lr'], anil_head=head)     # warm-up
+    state = mo.new_adam_state(params)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        out = mo.meta_iteration(params, X, Y, ospec, inner_steps, INNER_LR)
-        state = mo.new_adam_state(params)
+        out = mo.meta_iteration(params, X, Y, ospec, inner_steps, cfg['inner_lr'], anil_head=head)
         mo.adam_step(params, [g / tasks for g in out['grad']], state, lr=OUTER_LR)
         times.append(time.perf_counter() - t0)
     return tasks / (sum(times) / len(times)), cores, times
@@ -126,19 +168,20 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample_tasks = 2
-    times_all = []
-    for _ in range(args.warmup):
-        pass        # the warm-up task inside cpu_reference_rate covers lazy initialisation
-    rate, cores, times = cpu_reference_rate(sample_tasks, max(1, args.steps), args.inner_steps)
-    times_all += times
-    ms = 1000.0 * sum(times_all) / len(times_all)
-    sample = '%d-task sample of the 32-task meta-batch per step, fp32, %d torch threads' % (sample_tasks, cores)
+    cfg = CONFIGS[args.config]
+    T = args.inner_steps or cfg['steps']
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    sample_tasks = cfg['batch'] if args.config == 1 else 4         # cfg 1 whole batch, else 4 tasks
+    rate, cores, times = cpu_reference_rate(cfg, sample_tasks, max(1, args.steps), T)
+    ms = 1000.0 * sum(times) / len(times)
+    sample = ('%d-task sample of the %d-task meta-batch per step (1-task warm-up), fp32, %d torch threads, oracle port '
+              'of the reference path' % (sample_tasks, cfg['batch'], cores))
+    per = cfg['batch'] // world if args.scaling == 'strong' else cfg['batch']
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'tasks/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': cfg['metric'], 'value': rate, 'unit': 'tasks/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'inner_steps': args.inner_steps, 'sample': sample},
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_dict(cfg, args, world, per, args.scaling),
         'cpu_baseline': {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': 'tasks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -230,13 +273,38 @@ def program_work(engine):
     return work
 
 
+def build_trainer(cfg, tasks, T, dev, fast_tf32=False):
+    """Trainer + flat initial parameters of one BASELINE config at ``tasks`` tasks per GPU."""
+    import torch
+    from exploring_meta_b200 import spec as pspec
+    from exploring_meta_b200.trainer import AnilTrainer, MamlTrainer
+    ways, shots = cfg['ways'], cfg['shots']
+    if cfg['algo'] == 'anil':
+        spec = pspec.anil_body_spec(cfg['kind'], ways)
+        tr = AnilTrainer(spec, tasks, shots, T, cfg['inner_lr'], OUTER_LR, device=dev, use_graph=True)
+        body = pspec.init_flat_params(spec, seed=42)              # leaves the RNG after the blocks, like the reference
+        head = torch.nn.Linear(tr.engine.D, ways)
+        tr.theta_all.copy_(torch.cat([body, head.weight.detach().reshape(-1), head.bias.detach().reshape(-1)]))
+    else:
+        spec = pspec.omniglot_spec(ways) if cfg['kind'] == 'omni' else pspec.miniimagenet_spec(ways)
+        tr = MamlTrainer(spec, tasks, shots, T, cfg['inner_lr'], OUTER_LR, device=dev, use_graph=True)
+        tr.theta.copy_(pspec.init_flat_params(spec, seed=42))
+    return spec, tr
+
+
+def flops_per_task(cfg, spec, T):
+    if cfg['algo'] == 'anil':      # body forward + first-order backward over 2S rows (SURVEY 8(d): 27.93 GFLOP)
+        m = [hz * wz * spec.hidden * cin * 9 for (cin, _h, _w, hz, wz, _hp, _wp) in spec.block_dims()]
+        rows = 2 * cfg['ways'] * cfg['shots']
+        return 2.0 * rows * (2 * m[0] + 3 * sum(m[1:]))
+    return float(spec.flops_per_train_task(cfg['shots'], T))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from exploring_meta_b200 import _lib
-    from exploring_meta_b200 import spec as pspec
     from exploring_meta_b200.synthetic import make_tasks
-    from exploring_meta_b200.trainer import MamlTrainer
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -261,54 +329,67 @@ def run_ours(args):
     lib = _lib.load()
     lib.xm_set_precision(0 if args.fast_tf32 else 1)
 
-    spec = pspec.miniimagenet_spec(WAYS)
-    T = args.inner_steps
-    tr = MamlTrainer(spec, args.tasks, SHOTS, T, INNER_LR, OUTER_LR, device=dev, use_graph=True)
-    tr.theta.copy_(pspec.init_flat_params(spec, seed=42))
-    # two synthetic meta-batches per rank in pinned host memory (seed = data 0 + rank*1000 + batch)
-    host = []
-    for b in range(2):
-        X, Y = make_tasks(args.tasks, WAYS, SHOTS, (3, 84, 84), seed=rank * 1000 + b)
-        host.append((X.pin_memory(), Y.pin_memory()))
-    e = tr.engine
-    e.x.copy_(host[0][0]); e.y.copy_(host[0][1])
-    l0 = int(lib.xm_launch_count())
-    e.prog.replay(torch.cuda.current_stream().cuda_stream)          # eager replay: counts kernels per step
-    torch.cuda.synchronize()
-    kernels_per_step = int(lib.xm_launch_count()) - l0 + 1          # + Adam
+    cfg = CONFIGS[args.config]
+    T = args.inner_steps or cfg['steps']
+    ways, shots, shape = cfg['ways'], cfg['shots'], IN_SHAPE[cfg['kind']]
+    if args.tasks:
+        per = args.tasks
+    elif args.scaling == 'strong':
+        if cfg['batch'] % world:
+            raise SystemExit('global meta-batch %d is not divisible by %d ranks' % (cfg['batch'], world))
+        per = cfg['batch'] // world
+    else:
+        per = cfg['batch']
+    global_tasks = per * world
+
+    def host_batches(per_gpu):
+        """Two synthetic meta-batches in pinned host memory.  Strong scaling: rank r's shard [r*per, (r+1)*per) of
+        the SAME seeded global batch a single GPU would process; weak: one batch per rank."""
+        out = []
+        for b in range(2):
+            if args.scaling == 'strong' and per_gpu == per and not args.tasks:
+                X, Y = make_tasks(global_tasks, ways, shots, shape, seed=b)
+                X, Y = X[rank * per:(rank + 1) * per].contiguous(), Y[rank * per:(rank + 1) * per].contiguous()
+            else:
+                X, Y = make_tasks(per_gpu, ways, shots, shape, seed=rank * 1000 + b)
+            out.append((X.pin_memory(), Y.pin_memory()))
+        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step():
-        # inputs already in HBM (engine.x / engine.y): launch program (graph) + reduce + Adam
-        if tr.use_graph:
-            e.capture()
-        e.launch()
-        tr.flat[e.P] = e.loss.sum()
-        tr.flat[e.P + 1] = e.correct.sum()
-        tr._reduce_and_step(tr.theta, tr.tasks * tr.world)
-
-    for _ in range(max(args.warmup, 3)):
-        resident_step()
-    barrier()
-
-    def timed_region():
+    def time_resident(tr, steps, warmup, clocks=False):
+        """W warm-up + K timed device-resident steps (whole step = one CUDA graph), max over ranks."""
+        for _ in range(warmup):
+            tr.step_resident()
+        barrier()
         sampler = ClockSampler(local)
-        if rank == 0:
+        if rank == 0 and clocks:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for _ in range(args.steps):
-            resident_step()
+        for _ in range(steps):
+            tr.step_resident()
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), (sampler.stop() if rank == 0 else None)
+        return float(ms.item()), (sampler.stop() if (rank == 0 and clocks) else None)
+
+    mem0 = torch.cuda.memory_allocated(dev)
+    spec, tr = build_trainer(cfg, per, T, dev)
+    working_set_mb = (torch.cuda.memory_allocated(dev) - mem0) / 1e6
+    host = host_batches(per)
+    e = tr.engine
+    e.x.copy_(host[0][0]); e.y.copy_(host[0][1])
+    l0 = int(lib.xm_launch_count())
+    tr.step_eager()                                                 # un-captured step: counts OUR kernels per step
+    torch.cuda.synchronize()
+    kernels_per_step = int(lib.xm_launch_count()) - l0
+    warmup = max(args.warmup, 3)
 
     def throttled(c):
         bad = {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'} & set(c.get('reasons') or [])
@@ -316,20 +397,20 @@ def run_ours(args):
                  and c['sm_mhz'] < 0.75 * c['sm_max_mhz'])          # clocks well below max with no reason: leftover lock
         return bool(bad or stuck)
 
-    total_ms, clocks = timed_region()
+    total_ms, clocks = time_resident(tr, args.steps, warmup, clocks=True)
     # a measurement taken under a thermal / hardware slowdown (or a leftover clock lock) is rejected and taken once more
     redo = torch.tensor([1 if (rank == 0 and throttled(clocks)) else 0], device=dev)
     if world > 1:
         dist.all_reduce(redo, op=dist.ReduceOp.MAX)
     if int(redo.item()):
         first = clocks
-        total_ms, clocks = timed_region()
+        total_ms, clocks = time_resident(tr, args.steps, 1, clocks=True)
         if rank == 0:
             clocks['remeasured_after'] = first
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # ---- end to end through the public API: every step copies ITS pinned host batch to the device (stage(), a side
     # stream: the copy of batch i+1 overlaps the adaptation of batch i) and reads its loss / accuracy back ---------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tr.stage(*host[0])
     for i in range(2):
         tr.stage(*host[(i + 1) % 2])
@@ -348,36 +429,60 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item())
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
-    d2h = args.tasks * 8
+    d2h = per * 8
+    if tr.comm is not None:
+        tr.comm.check()
+
+    # ---- weak-scaling leg of a strong N > 1 run (kept as an extra key) ------------------------------------------
+    weak = None
+    if world > 1 and args.scaling == 'strong' and not args.tasks and not args.no_weak:
+        del tr, e
+        torch.cuda.empty_cache()
+        _spec, trw = build_trainer(cfg, cfg['batch'], T, dev)
+        Xw, Yw = make_tasks(cfg['batch'], ways, shots, shape, seed=rank * 1000)
+        trw.engine.x.copy_(Xw); trw.engine.y.copy_(Yw)
+        wms, _ = time_resident(trw, args.steps, warmup)
+        weak = {'tasks_per_gpu': cfg['batch'], 'global_meta_batch': cfg['batch'] * world,
+                'value': cfg['batch'] * world * args.steps / (wms / 1000.0), 'unit': 'tasks/s',
+                'ms_per_step': wms / args.steps}
+        tr = trw
+        e = trw.engine
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    global_tasks = args.tasks * world
     value = global_tasks * args.steps / (total_ms / 1000.0)
     e2e = global_tasks * args.steps / (e2e_ms / 1000.0)
     peaks = measured_peaks()
-    flops_per_task = spec.flops_per_train_task(SHOTS, T)
+    fpt = flops_per_task(cfg, spec, T)
+    in_mb = h2d / 1e6
+    cd = config_dict(cfg, args, world, per, args.scaling)
+    run_info = {'tasks_per_gpu': per, 'working_set_mb_per_gpu': round(working_set_mb, 1),
+               'parallelism': ('tasks sharded over %d GPU(s); the %d-float [meta-grad ; loss ; correct ; BN partials] '
+                               'buffers are summed over NVLink peer memory inside the Adam kernel (no NCCL call)'
+                               % (world, tr.flat.numel())) if world > 1 else 'single GPU',
+               'l2_policy': 'no explicit flush: every step streams its inputs (%.1f MB/GPU) and the saved activations of '
+                            'all inner steps (static buffers: %.0f MB/GPU, each written and re-read once per step) '
+                            'through the 126 MB L2' % (in_mb, working_set_mb),
+               'cuda_graph': 'whole step (launch program + shard sums + allreduce + Adam + BN EMA) is one graph'}
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'tasks/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None,
+        'metric': cfg['metric'], 'value': value, 'unit': 'tasks/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+        'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32 (tensor-core contractions: %s)' % ('1xTF32' if args.fast_tf32 else '3xTF32 error-compensated, fp32 accumulate'),
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'tasks_per_gpu': args.tasks, 'global_meta_batch': global_tasks,
-                   'inner_steps': T, 'inner_lr': INNER_LR, 'ways': WAYS, 'shots': SHOTS,
-                   'parallelism': 'tasks sharded over %d GPU(s), one fp32 allreduce of %d floats per step' % (world, tr.flat.numel()),
-                   'l2_policy': 'inputs (135.5 MB/step) and activations (several GB/step) exceed the 126 MB L2; no explicit flush',
-                   'cuda_graph': bool(tr.use_graph)},
+        'config': cd, 'run': run_info,
         'e2e': {'value': e2e, 'unit': 'tasks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': kernels_per_step * args.steps,
         'clocks': clocks,
-        'algorithmic_tflops': value * flops_per_task / 1e12,
-        'flops_per_task': flops_per_task,
+        'algorithmic_tflops': value * fpt / 1e12,
+        'flops_per_task': fpt,
     }
+    if weak is not None:
+        line['weak_scaling'] = weak
 
     if world == 1 and not args.no_kernel_breakdown:
         times = kernel_breakdown(e)
@@ -417,28 +522,35 @@ def run_ours(args):
                 traffic = json.load(f)
         top = max(times.items(), key=lambda kv: kv[1]['ms'])[0]
         tv, w = times[top], work.get(top, {'flops': 0.0, 'bytes': 0.0})
-        tr = traffic.get(top, {}).get('dram_bytes_per_launch')
+        trf = traffic.get(top, {}).get('dram_bytes_per_launch') if args.config == 2 else None
         if hbm_bound(top):
             achieved = w['bytes'] / tv['ms'] / 1e6
             line['roofline'] = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
-                                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': tr,
+                                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': trf,
+                                'traffic_source': traffic.get('_meta'),
                                 'peak_source': peaks['source'] + ' copy bandwidth (MEASURED_PEAKS.json)',
                                 'algorithmic_bytes_per_launch': w['bytes'] / tv['calls'],
                                 'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
         else:
             achieved = w['flops'] / tv['ms'] / 1e9
             line['roofline'] = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_tflops'],
-                                'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': tr,
+                                'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'], 'traffic': trf,
+                                'traffic_source': traffic.get('_meta'),
                                 'peak_source': peaks['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json); the '
                                 'kernel computes fp32-grade products as 3 TF32 tcgen05.mma each (TF32 dense = 1/2 of the bf16 '
                                 'rate), so its own ceiling is 1/6 of this peak (DESIGN.md section 4)',
                                 'algorithmic_flops_per_launch': w['flops'] / tv['calls'],
                                 'launches_per_step': tv['calls'], 'avg_launch_ms': tv['ms'] / tv['calls']}
     if world == 1 and not args.no_cpu_baseline:
-        rate, cores, times = cpu_reference_rate(2, 2, T)
+        n_sample = cfg['batch'] if args.config == 1 else 4
+        rate, cores, times = cpu_reference_rate(cfg, n_sample, 3 if args.config == 1 else 2, T)
+        rate1, _c, _t = cpu_reference_rate(cfg, 1, 1, T, threads=1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port',
-                                'sample': '2-task sample x 2 repetitions after a 1-task warm-up, fp32, '
-                                          '%d torch threads (oracle port of the reference path)' % cores}
+                                'sample': '%d-task sample x %d repetitions after a 1-task warm-up, fp32, %d torch '
+                                          'threads (oracle port of the reference path, BASELINE.md 3.4)'
+                                          % (n_sample, len(times), cores),
+                                'one_thread': {'value': rate1, 'unit': 'tasks/s', 'cores': 1,
+                                               'sample': '1 task x 1 repetition after a 1-task warm-up'}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -106,6 +106,15 @@ class XmAnilHeadArgs(Structure):
                 ('scratch', c_void_p), ('scratch_bytes', c_int64)]
 
 
+class XmAdamArgs(Structure):
+    _fields_ = [('theta', c_void_p), ('m', c_void_p), ('v', c_void_p), ('n_params', c_int64),
+                ('local', c_void_p), ('reduced', c_void_p), ('n_total', c_int64),
+                ('grad_scale', c_float), ('lr', c_float), ('beta1', c_float), ('beta2', c_float), ('eps', c_float),
+                ('step', c_void_p)]
+
+
+XM_COMM_MAX_WORLD, XM_IPC_HANDLE_BYTES = 8, 64
+
 # name -> (restype, argtypes): every symbol include/xmeta.h declares.
 SYMBOLS = {
     'xm_conv': (c_int32, [POINTER(XmConvArgs), c_void_p]),
@@ -132,6 +141,12 @@ SYMBOLS = {
     'xm_accumulate_tasks': (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p]),
     'xm_adam_step': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                c_float, c_float, c_float, c_int32, c_void_p]),
+    'xm_comm_create': (c_int32, [c_int32, c_int32, c_int64, POINTER(c_void_p), c_void_p]),
+    'xm_comm_connect': (c_int32, [c_void_p, c_void_p]),
+    'xm_comm_error': (c_int32, [c_void_p]),
+    'xm_comm_destroy': (c_int32, [c_void_p]),
+    'xm_allreduce_adam': (c_int32, [c_void_p, POINTER(XmAdamArgs), c_void_p]),
+    'xm_finish_shard': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     'xm_bn_ema': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int32,
                             c_float, c_void_p]),
     'xm_set_precision': (c_int32, [c_int32]),

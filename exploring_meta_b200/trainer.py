@@ -7,6 +7,9 @@ captured launch program over the rank's shard of tasks; with ``world_size > 1`` 
 are combined by ONE sum-allreduce of the flat fp32 buffer [meta-grad ; loss sum ; correct count]
 (NCCL over NVLink) before the identical, replicated Adam step.  Nothing here synchronises the host.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -25,10 +28,20 @@ class _TrainerBase:
         self.iteration = 0
         self.use_graph = bool(use_graph)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        # flat fp32 buffer that is all-reduced: [grad (total_params) ; loss sum ; correct count ; BN EMA partials (extra)]
+        # flat fp32 buffer that is summed over ranks: [grad (total_params) ; loss sum ; correct count ; BN EMA partials
+        # (extra)].  ``flat`` is this rank's contribution, ``red`` the sum (what Adam and metrics() read).
         self.flat = torch.zeros(total_params + 2 + extra, dtype=torch.float32, device=self.device)
+        self.red = torch.zeros_like(self.flat)
         self.m = torch.zeros(total_params, dtype=torch.float32, device=self.device)
         self.v = torch.zeros(total_params, dtype=torch.float32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)    # Adam step count, advanced on device
+        self._graphs = {}
+        # transport of the shard sums: 'p2p' = inside the Adam kernel over NVLink peer memory (csrc/comm.cu), 'dist' =
+        # torch.distributed all_reduce (what the gloo / CPU-emulator tests use; XM_COMM=nccl selects it on GPUs)
+        self.comm = None
+        if self.world > 1 and self.device.type == 'cuda' and os.environ.get('XM_COMM', 'p2p') == 'p2p':
+            from .comm import PeerComm
+            self.comm = PeerComm(self.flat.numel(), self.device)
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
@@ -67,13 +80,70 @@ class _TrainerBase:
         self._consumed[slot].record(cur)
 
     def _reduce_and_step(self, theta_all, global_tasks):
-        if self.world > 1:
+        """Shard sums -> (sum over ranks) -> Adam, all on the current stream and graph-capturable: the Adam step
+        number lives in device memory (``step_dev``)."""
+        e, n = self.engine, theta_all.numel()
+        stream = self._stream()
+        _lib.check(self.lib.xm_finish_shard(_p(e.loss), e.correct.data_ptr(), self.tasks, _p(self.flat, n),
+                                            self.step_dev.data_ptr(), stream), 'xm_finish_shard')
+        local = self.flat
+        if self.world > 1 and self.comm is None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        a = _lib.XmAdamArgs()
+        a.theta, a.m, a.v, a.n_params = _p(theta_all), _p(self.m), _p(self.v), n
+        a.local, a.reduced, a.n_total = _p(local), _p(self.red), self.flat.numel()
+        a.grad_scale, a.lr = 1.0 / global_tasks, self.outer_lr
+        a.beta1, a.beta2, a.eps = ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS
+        a.step = self.step_dev.data_ptr()
+        self._adam_args = a                       # keep the block alive
+        _lib.check(self.lib.xm_allreduce_adam(self.comm.ptr if self.comm is not None else None, ctypes.byref(a),
+                                              stream), 'xm_allreduce_adam')
+
+    def _run(self, key, body):
+        """Runs ``body()`` (engine program + outer step) -- through a CUDA graph captured on first use when enabled."""
+        if not (self.use_graph and self.device.type == 'cuda'):
+            return body()
+        g = self._graphs.get(key)
+        if g is None:
+            e = self.engine
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                e.prog.replay(side.cuda_stream)                # warm-up (idempotent): loads every kernel of the program
+                self._warm_outer(side.cuda_stream)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+        g.replay()
+
+    def step_resident(self):
+        """One meta-iteration on the batch already in ``engine.x`` / ``engine.y`` (no input copy)."""
+        self._run('resident', self._step_body)
+        self._count_step()
+
+    def step_eager(self):
+        """Same, launching kernel by kernel (no graph): used to count launches and by per-kernel timing."""
+        self._step_body()
+        self._count_step()
+
+    def _count_step(self):
         self.iteration += 1
-        n = theta_all.numel()
-        _lib.check(self.lib.xm_adam_step(_p(theta_all), _p(self.flat), _p(self.m), _p(self.v), n,
-                                         1.0 / global_tasks, self.outer_lr, ADAM_BETAS[0], ADAM_BETAS[1],
-                                         ADAM_EPS, self.iteration, self._stream()), 'xm_adam_step')
+
+    def _warm_outer(self, stream):
+        """Loads the outer-step kernels on throw-away buffers (a warm-up of the real ones would apply an update)."""
+        t = torch.zeros(8, dtype=torch.float32, device=self.device)
+        c = torch.zeros(1, dtype=torch.int32, device=self.device)
+        st = torch.ones(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.xm_finish_shard(_p(t), c.data_ptr(), 1, _p(t, 4), st.data_ptr(), stream), 'xm_finish_shard')
+        a = _lib.XmAdamArgs()
+        a.theta, a.m, a.v, a.n_params = _p(t), _p(t, 2), _p(t, 4), 2
+        a.local, a.reduced, a.n_total = _p(t, 6), _p(t, 6), 2
+        a.grad_scale, a.lr, a.beta1, a.beta2, a.eps, a.step = 1.0, 0.0, 0.9, 0.999, 1e-8, st.data_ptr()
+        _lib.check(self.lib.xm_allreduce_adam(None, ctypes.byref(a), stream), 'xm_allreduce_adam')
+        torch.cuda.synchronize(self.device)
 
 
 class MamlTrainer(_TrainerBase):
@@ -116,20 +186,26 @@ class MamlTrainer(_TrainerBase):
         else:
             e.x.copy_(x, non_blocking=True)
             e.y.copy_(y, non_blocking=True)
-        if self.use_graph and self.device.type == 'cuda':
-            e.capture()
-        e.launch()
-        P = e.P
-        self.flat[P] = e.loss.sum()
-        self.flat[P + 1] = e.correct.sum()
+        key = 'resident' if track_running_stats else 'no_stats'
+        self._run(key, lambda: self._step_body(track_running_stats))
+        self._count_step(track_running_stats)
+        return e.loss, e.correct
+
+    def _count_step(self, track_running_stats=True):
+        self.iteration += 1
+        if track_running_stats:
+            self.num_batches_tracked += self.tasks * (self.engine.steps + 1) * self.world
+
+    def _step_body(self, track_running_stats=True):
+        e = self.engine
+        e.prog.replay(self._stream())
         if track_running_stats and self.world == 1:
-            self.num_batches_tracked += e.update_running_stats(self.running_mean, self.running_var)
+            e.update_running_stats(self.running_mean, self.running_var)
         elif track_running_stats:
             self._stage_running_stats()
         self._reduce_and_step(self.theta, self.tasks * self.world)
         if track_running_stats and self.world > 1:
             self._apply_running_stats()
-        return e.loss, e.correct
 
     # The reference's shared BN buffers see one EMA update r <- (1-m) r + m s per forward call, task after task
     # (vision/maml_vision.py:102-112 through learn2learn's clones).  The recurrence is linear: over the N calls of the
@@ -151,15 +227,14 @@ class MamlTrainer(_TrainerBase):
         from .engine import BN_MOMENTUM
         calls = self.tasks * (e.steps + 1) * self.world
         decay = (1.0 - BN_MOMENTUM) ** calls
-        tail = self.flat[e.P + 2:].view(L, 2, C)
+        tail = self.red[e.P + 2:].view(L, 2, C)
         for l in range(L):
             self.running_mean[l].mul_(decay).add_(tail[l, 0])
             self.running_var[l].mul_(decay).add_(tail[l, 1])
-        self.num_batches_tracked += calls
 
     def metrics(self):
         P, n = self.engine.P, self.tasks * self.world
-        return self.flat[P] / n, self.flat[P + 1] / (n * self.engine.S)
+        return self.red[P] / n, self.red[P + 1] / (n * self.engine.S)
 
 
 class AnilTrainer(_TrainerBase):
@@ -192,15 +267,14 @@ class AnilTrainer(_TrainerBase):
         else:
             e.x.copy_(x, non_blocking=True)
             e.y.copy_(y, non_blocking=True)
-        if self.use_graph and self.device.type == 'cuda':
-            e.capture()
-        e.launch()
-        n = e.P + e.PH
-        self.flat[n] = e.loss.sum()
-        self.flat[n + 1] = e.correct.sum()
-        self._reduce_and_step(self.theta_all, self.tasks * self.world)
+        self._run('resident', self._step_body)
+        self._count_step()
         return e.loss, e.correct
+
+    def _step_body(self):
+        self.engine.prog.replay(self._stream())
+        self._reduce_and_step(self.theta_all, self.tasks * self.world)
 
     def metrics(self):
         n, g = self.engine.P + self.engine.PH, self.tasks * self.world
-        return self.flat[n] / g, self.flat[n + 1] / (g * self.engine.S)
+        return self.red[n] / g, self.red[n + 1] / (g * self.engine.S)

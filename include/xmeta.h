@@ -14,8 +14,10 @@
  *  - Every function returns 0 on success, <0 for an invalid argument (message via xm_last_error()),
  *    >0 = cudaError_t of a failed launch.  No exceptions, no exit/abort.
  *  - Every function is asynchronous on the given stream (cudaStream_t passed as void*), does no
- *    host synchronisation and is CUDA-graph capturable.  No global mutable state except the
- *    thread-local last-error string.
+ *    host synchronisation and is CUDA-graph capturable.  Process-wide mutable state: the thread-local last-error
+ *    string, the launch counter, the two A/B switches xm_set_precision / xm_set_tcgen05 (read at launch time),
+ *    and per-device caches of the SM count / kernel attributes.  XmComm (below) is the only object that owns
+ *    device memory.
  *  - "task" = one few-shot task of the meta-batch.  Every tensor carries a leading task dimension and
  *    every parameter pointer a per-task stride in floats (stride 0 = all tasks share the master
  *    weights, as at inner step 0 and for the ANIL body).
@@ -260,6 +262,42 @@ int xm_accumulate_tasks(const float* src, int64_t task_stride, int32_t tasks, in
  * torch.optim.Adam's update with bias correction for step number `step` (1-based), no weight decay. */
 int xm_adam_step(float* theta, const float* grad, float* m, float* v, int64_t count, float grad_scale,
                  float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* ---- sharded outer step ------------------------------------------------------------
+ * The reference sums the tasks' gradients into the master .grad inside one process (vision/maml_vision.py:112) and
+ * steps Adam (:139-141).  With the meta-batch sharded over GPUs (one process per GPU) the shard sums are combined
+ * over NVLink peer memory INSIDE the Adam kernel: no NCCL call, one launch, graph-capturable.
+ *
+ * XmComm is the one object of this library that owns device memory: a staging / flag block per rank, exported with
+ * cudaIpcGetMemHandle.  xm_comm_create fills handle_out[XM_IPC_HANDLE_BYTES]; the caller exchanges the handles of
+ * all ranks out of band (rank order) and passes the world * XM_IPC_HANDLE_BYTES bytes to xm_comm_connect.
+ * n_floats = length of the flat buffer every later xm_allreduce_adam call reduces.  xm_comm_error returns 1 after a
+ * peer failed to arrive within ~4 s (the kernel gives up instead of hanging the GPU), -1 on a CUDA error. */
+#define XM_COMM_MAX_WORLD 8
+#define XM_IPC_HANDLE_BYTES 64
+typedef struct XmComm XmComm;
+int xm_comm_create(int32_t world, int32_t rank, int64_t n_floats, XmComm** out, unsigned char* handle_out);
+int xm_comm_connect(XmComm* comm, const unsigned char* handles);
+int xm_comm_error(XmComm* comm);
+int xm_comm_destroy(XmComm* comm);
+
+/* xm_allreduce_adam: reduced[i] = sum over ranks (rank order) of local[i], i < n_total; then for i < n_params
+ * torch.optim.Adam's update of theta / m / v with g = reduced[i] * grad_scale and the bias correction of step
+ * number *step (1-based, device memory: advanced by xm_finish_shard, so a captured graph replays correctly).
+ * comm == NULL (or world 1): reduced = local, single-GPU outer step.  Every rank must issue the same sequence of
+ * calls on its communicator. */
+typedef struct XmAdamArgs {
+  float* theta; float* m; float* v; int64_t n_params;
+  const float* local; float* reduced; int64_t n_total;
+  float grad_scale, lr, beta1, beta2, eps;
+  const int32_t* step;
+} XmAdamArgs;
+int xm_allreduce_adam(XmComm* comm, const XmAdamArgs* a, void* stream);
+
+/* out2[0] = sum_t loss[t], out2[1] = sum_t correct[t] (the driver's running sums, vision/maml_vision.py:113-115),
+ * *step += 1 (step may be NULL). */
+int xm_finish_shard(const float* loss, const int32_t* correct, int32_t tasks, float* out2, int32_t* step,
+                    void* stream);
 
 /* BatchNorm running-statistics side effect, composed sequentially like the reference's shared
  * buffers see it: for o in [0,n_outer) for i in [0,n_inner): r <- (1-m) r + m s(o,i), where

@@ -629,6 +629,30 @@ class EmulatedLib:
         th.copy_(th - (lr / (1 - beta1 ** step)) * mm / denom)
         return 0
 
+    def xm_finish_shard(self, loss, correct, tasks, out2, step, stream):
+        self.launches += 1
+        o = view(out2, (2,))
+        l, c = view(loss, (tasks,)), view(correct, (tasks,), torch.int32)
+        s = torch.zeros((), dtype=torch.float32)
+        k = torch.zeros((), dtype=torch.float32)
+        for t in range(tasks):
+            s = s + l[t]
+            k = k + c[t].float()
+        o[0], o[1] = s, k
+        if step:
+            view(step, (1,), torch.int32).add_(1)
+        return 0
+
+    def xm_allreduce_adam(self, comm, ref, stream):
+        """Single-rank contract only (comm NULL): reduced = local, then Adam on the first n_params entries."""
+        assert not comm, 'the emulator has no peer-memory transport'
+        a = self._args(ref)
+        red = view(a.reduced, (a.n_total,))
+        red.copy_(view(a.local, (a.n_total,)).clone())
+        step = int(view(a.step, (1,), torch.int32)[0])
+        return self.xm_adam_step(a.theta, a.reduced, a.m, a.v, a.n_params, a.grad_scale, a.lr, a.beta1, a.beta2,
+                                 a.eps, step, stream)
+
     def xm_bn_ema(self, rm, rv, stats, n_outer, outer_stride, n_inner, inner_stride, C, momentum, stream):
         self.launches += 1
         m, v = view(rm, (C,)), view(rv, (C,))
