@@ -10,6 +10,7 @@
 // Reference ops replaced: aten::linear + cross_entropy fwd/bwd/double-bwd (core_functions/vision_models.py:107-110,
 // :51-55; vision/maml_vision.py:86), accuracy (core_functions/vision.py:21-23), and for ANIL the whole
 // fast_adapt loop on features (core_functions/vision.py:9-17 with features != None).
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace xm {
@@ -101,101 +102,139 @@ struct HeadK {
   float scale;
 };
 
-// Feature rows in their NATIVE order: Xn(i, e) with e = s*c + ch for mode 0 (the NHWC element order, so a warp
-// reads 128 B lines) and e = ch for mode 1 (spatial mean).  The weights are permuted once into shared memory to
-// the same order: Wn[w][e] = W[w][ch*hw + s].
-struct NFeat {
-  const float* f; int hw, c, mode, De;
-  __device__ __forceinline__ float at(int i, int e) const {
-    if (mode == 0) return __ldg(f + (long long)i * De + e);
-    float acc = 0.f;
-    for (int s = 0; s < hw; ++s) acc += __ldg(f + ((long long)i * hw + s) * c + e);
-    return acc / (float)hw;
-  }
-};
+// head_kernel: one thread-block CLUSTER per task (G <= 8 CTAs).  CTA r owns a slice of the feature index range in the
+// features' NATIVE order (e = s*c + ch for the NHWC flatten, e = ch for the spatial mean) and keeps ONLY that slice
+// of the rows, the weights and their tangents in shared memory (one coalesced load, all requests in flight at once):
+//   1. partial logits of the slice (and their tangent) -> own shared memory
+//   2. cluster barrier; every CTA sums the G partials in rank order through distributed shared memory
+//   3. softmax / cross-entropy / dL/dlogits (+ tangent through the softmax Hessian) redundantly per CTA (tiny)
+//   4. parameter-gradient (axpy epilogue = fused SGD step) and feature-gradient of the slice from shared memory
+// The kernel's latency is a few global round trips whatever the task count (it was ~100 serialized L2 round trips:
+// 76-100 us per call, 1 ms of the config-2 step and the largest single item at 4 tasks per GPU).
+namespace cg = cooperative_groups;
 
-// head_kernel: grid (tasks, G).  Every CTA of a task recomputes the (tiny) logits / softmax phase, then the
-// G CTAs split the parameter-gradient and feature-gradient phases over the feature index range -- no
-// inter-CTA synchronisation, G x the parallelism of one CTA per task.
-__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k) {
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k, const int G) {
   extern __shared__ float sm[];
-  const int task = blockIdx.x, part = blockIdx.y, nparts = gridDim.y, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = HEAD_THREADS / 32;
-  const int n = k.n, ways = k.ways, D = k.D;
-  float* logit = sm;                        // [n][ways]
-  float* prob = logit + n * ways;           // [n][ways]
-  float* gl = prob + n * ways;              // [n][ways]   dL/dlogits
-  float* ld = gl + n * ways;                // [n][ways]   tangent of logits        (dual)
-  float* gld = ld + n * ways;               // [n][ways]   tangent of dL/dlogits    (dual)
-  float* row_loss = gld + n * ways;         // [n]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int task = blockIdx.x / G, part = blockIdx.x - task * G, tid = threadIdx.x;
+  const int n = k.n, ways = k.ways, D = k.D, nw = n * ways;
+  const int e_lo = (int)((long long)D * part / G), e_hi = (int)((long long)D * (part + 1) / G);
+  const int span = e_hi - e_lo;
+  const int span_max = (D + G - 1) / G + 1;     // same carve-up in every CTA of the cluster (DSMEM offsets must agree)
+  const int ld = span_max | 1;                   // odd row stride: conflict-free column walks
+  const bool dual = k.dual != 0, have_xd = dual && k.feat_dot;
+  float* part_l = sm;                        // [nw]   partial logits of this slice          (read by the peers)
+  float* part_d = part_l + nw;               // [nw]   partial tangent logits                (read by the peers)
+  float* logit = part_d + nw;                // [nw]
+  float* ldot = logit + nw;                  // [nw]
+  float* prob = ldot + nw;                   // [nw]
+  float* gl = prob + nw;                     // [nw]   dL/dlogits
+  float* gld = gl + nw;                      // [nw]   its tangent
+  float* row_loss = gld + nw;                // [n]
   int* row_ok = reinterpret_cast<int*>(row_loss + n);   // [n]
-  float* Wn = row_loss + 2 * n;             // [ways][D]   native order
-  float* Wdn = Wn + ways * D;               // [ways][D]   (dual)
+  float* Xs = row_loss + 2 * n;              // [n][ld]
+  float* Xd = Xs + (size_t)n * ld;           // [n][ld]      (have_xd)
+  float* Wn = Xd + (have_xd ? (size_t)n * ld : 0);       // [ways][ld]
+  float* Wdn = Wn + (size_t)ways * ld;       // [ways][ld]   (dual)
 
   const long long fbase = (long long)task * n * k.hw * k.c;
-  const NFeat X{k.feat + fbase, k.hw, k.c, k.mode, D};
-  const NFeat Xd{k.feat_dot ? k.feat_dot + fbase : nullptr, k.hw, k.c, k.mode, D};
-  const bool have_xd = k.dual && k.feat_dot;
+  const float* F = k.feat + fbase;
+  const float* Fd = have_xd ? k.feat_dot + fbase : nullptr;
   const float* W = k.w + (long long)task * k.wb_stride;
   const float* B = k.b + (long long)task * k.wb_stride;
-  const float* Wd = k.dual ? k.w_dot + (long long)task * k.wbdot_stride : nullptr;
-  const float* Bd = k.dual ? k.b_dot + (long long)task * k.wbdot_stride : nullptr;
+  const float* Wd = dual ? k.w_dot + (long long)task * k.wbdot_stride : nullptr;
+  const float* Bd = dual ? k.b_dot + (long long)task * k.wbdot_stride : nullptr;
   const int64_t* lab = k.labels + (long long)task * k.labels_per_task;
+  auto perm = [&](int e) { return k.mode == 0 ? (e % k.c) * k.hw + e / k.c : e; };   // native -> PyTorch feature index
 
-  // native index e -> PyTorch feature index
-  auto perm = [&](int e) { return k.mode == 0 ? (e % k.c) * k.hw + e / k.c : e; };
-  for (int idx = tid; idx < ways * D; idx += HEAD_THREADS) {
-    const int w = idx / D, e = idx - w * D;
-    Wn[idx] = __ldg(W + (long long)w * D + perm(e));
-    if (k.dual) Wdn[idx] = __ldg(Wd + (long long)w * D + perm(e));
+  // ---- stage the slice ------------------------------------------------------------------------------------------
+  for (int idx = tid; idx < n * span; idx += HEAD_THREADS) {
+    const int i = idx / span, j = idx - i * span, e = e_lo + j;
+    float x, xd = 0.f;
+    if (k.mode == 0) {
+      x = __ldg(F + (long long)i * D + e);
+      if (have_xd) xd = __ldg(Fd + (long long)i * D + e);
+    } else {
+      x = 0.f;
+      for (int s = 0; s < k.hw; ++s) {
+        x += __ldg(F + ((long long)i * k.hw + s) * k.c + e);
+        if (have_xd) xd += __ldg(Fd + ((long long)i * k.hw + s) * k.c + e);
+      }
+      x /= (float)k.hw;
+      xd /= (float)k.hw;
+    }
+    Xs[i * ld + j] = x;
+    if (have_xd) Xd[i * ld + j] = xd;
+  }
+  for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+    const int w = idx / span, j = idx - w * span;
+    const long long src = (long long)w * D + perm(e_lo + j);
+    Wn[w * ld + j] = __ldg(W + src);
+    if (dual) Wdn[w * ld + j] = __ldg(Wd + src);
   }
   __syncthreads();
 
-  // ---- logits (and their tangent): one warp per row, 8 classes at a time ----------------------------------
-  for (int i = warp; i < n; i += nwarps) {
-    for (int w0 = 0; w0 < ways; w0 += 8) {
-      float acc[8], accd[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = accd[j] = 0.f;
-      for (int e = lane; e < D; e += 32) {
-        const float x = X.at(i, e);
-        const float xd = have_xd ? Xd.at(i, e) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (w0 + j < ways) {
-            const float wv = Wn[(w0 + j) * D + e];
-            acc[j] = fmaf(x, wv, acc[j]);
-            if (k.dual) accd[j] = fmaf(xd, wv, fmaf(x, Wdn[(w0 + j) * D + e], accd[j]));
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (w0 + j < ways) {
-          const float a = warp_sum(acc[j]);
-          if (lane == 0) logit[i * ways + w0 + j] = a + B[w0 + j];
-          if (k.dual) {
-            const float ad = warp_sum(accd[j]);
-            if (lane == 0) ld[i * ways + w0 + j] = ad + Bd[w0 + j];
-          }
-        }
+  // ---- partial logits of the slice: thread = (row, class) ---------------------------------------------------------
+  for (int o = tid; o < nw; o += HEAD_THREADS) {
+    const int i = o / ways, w = o - i * ways;
+    const float* xr = Xs + i * ld;
+    const float* wr = Wn + w * ld;
+    float acc = 0.f, accd = 0.f;
+    if (!dual) {
+      for (int j = 0; j < span; ++j) acc = fmaf(xr[j], wr[j], acc);
+    } else {
+      const float* wdr = Wdn + w * ld;
+      const float* xdr = Xd + i * ld;
+      for (int j = 0; j < span; ++j) {
+        acc = fmaf(xr[j], wr[j], acc);
+        accd = fmaf(xr[j], wdr[j], accd);
+        if (have_xd) accd = fmaf(xdr[j], wr[j], accd);
       }
     }
+    part_l[o] = acc;
+    part_d[o] = accd;
   }
-  __syncthreads();
-  softmax_rows(logit, lab, k.label_row0, k.label_row_step, n, ways, prob, row_loss, row_ok);
-  __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int y = (int)lab[k.label_row0 + (long long)i * k.label_row_step];
+  cluster.sync();
+  for (int o = tid; o < nw; o += HEAD_THREADS) {
+    const int w = o % ways;
+    float acc = 0.f, accd = 0.f;
+    for (int r = 0; r < G; ++r) {                       // rank order: every CTA of the cluster gets the same bits
+      const float* peer = cluster.map_shared_rank(part_l, r);
+      acc += peer[o];
+      if (dual) accd += peer[nw + o];
+    }
+    logit[o] = acc + B[w];
+    if (dual) ldot[o] = accd + Bd[w];
+  }
+  cluster.sync();                                       // peers have read this CTA's partials; logits visible below
+
+  // ---- softmax, loss, accuracy, dL/dlogits (+ tangent) ----------------------------------------------------------
+  for (int i = tid; i < n; i += HEAD_THREADS) {
+    const float* z = logit + i * ways;
+    float mx = z[0];
+    int arg = 0;
+    for (int w = 1; w < ways; ++w)
+      if (z[w] > mx) { mx = z[w]; arg = w; }
+    float se = 0.f;
+    for (int w = 0; w < ways; ++w) se += expf(z[w] - mx);
+    const float lse = mx + logf(se);
+    int y = (int)lab[k.label_row0 + (long long)i * k.label_row_step];
+    y = y < 0 ? 0 : (y >= ways ? ways - 1 : y);         // out-of-range labels are clamped (never index out of bounds)
     float pd = 0.f;
-    if (k.dual)
-      for (int w = 0; w < ways; ++w) pd += prob[i * ways + w] * ld[i * ways + w];
+    for (int w = 0; w < ways; ++w) {
+      const float p = expf(z[w] - lse);
+      prob[i * ways + w] = p;
+      if (dual) pd += p * ldot[i * ways + w];
+    }
     for (int w = 0; w < ways; ++w) {
       const float p = prob[i * ways + w];
       gl[i * ways + w] = (p - (w == y ? 1.f : 0.f)) / (float)n;
-      if (k.dual) gld[i * ways + w] = p * (ld[i * ways + w] - pd) / (float)n;
+      if (dual) gld[i * ways + w] = p * (ldot[i * ways + w] - pd) / (float)n;
     }
+    row_loss[i] = lse - z[y];
+    row_ok[i] = (arg == y) ? 1 : 0;
   }
+  __syncthreads();
   if (part == 0) {
     if (tid == 0) {
       float s = 0.f;
@@ -205,64 +244,46 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadK k) {
       if (k.correct) k.correct[task] = ok;
     }
     if (k.logits)
-      for (int i = tid; i < n * ways; i += blockDim.x) k.logits[(long long)task * n * ways + i] = logit[i];
+      for (int i = tid; i < nw; i += HEAD_THREADS) k.logits[(long long)task * nw + i] = logit[i];
   }
-  __syncthreads();
 
-  // this CTA's slice of the feature index range
-  const int e_lo = (int)((long long)D * part / nparts), e_hi = (int)((long long)D * (part + 1) / nparts);
-  const float* G = k.dual ? gld : gl;
-  // ---- parameter gradients through the axpy epilogue: thread = feature index e, all classes --------------
+  const float* Gq = dual ? gld : gl;
+  // ---- parameter gradients of the slice through the axpy epilogue: thread = (class, feature) ----------------------
   if (k.out_w) {
     float* OW = k.out_w + (long long)task * k.out_stride;
     float* OB = k.out_b + (long long)task * k.out_stride;
     const float* BW = k.base_w ? k.base_w + (long long)task * k.base_stride : nullptr;
     const float* BB = k.base_b ? k.base_b + (long long)task * k.base_stride : nullptr;
-    for (int e = e_lo + tid; e < e_hi; e += HEAD_THREADS) {
-      const int d = perm(e);
-      for (int w0 = 0; w0 < ways; w0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int i = 0; i < n; ++i) {
-          const float x = X.at(i, e);
-          const float xd = have_xd ? Xd.at(i, e) : 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (w0 + j < ways) {
-              acc[j] = fmaf(G[i * ways + w0 + j], x, acc[j]);
-              if (have_xd) acc[j] = fmaf(gl[i * ways + w0 + j], xd, acc[j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (w0 + j < ways) {
-            const long long idx = (long long)(w0 + j) * D + d;
-            OW[idx] = (BW ? BW[idx] : 0.f) + k.scale * acc[j];
-          }
+    for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+      const int w = idx / span, j = idx - w * span;
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) {
+        acc = fmaf(Gq[i * ways + w], Xs[i * ld + j], acc);
+        if (have_xd) acc = fmaf(gl[i * ways + w], Xd[i * ld + j], acc);
       }
+      const long long dst = (long long)w * D + perm(e_lo + j);
+      OW[dst] = (BW ? BW[dst] : 0.f) + k.scale * acc;
     }
     if (part == 0)
-      for (int w = tid; w < ways; w += blockDim.x) {
+      for (int w = tid; w < ways; w += HEAD_THREADS) {
         float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc += G[i * ways + w];
+        for (int i = 0; i < n; ++i) acc += Gq[i * ways + w];
         OB[w] = (BB ? BB[w] : 0.f) + k.scale * acc;
       }
   }
-  // ---- feature gradient (native order: coalesced stores) ---------------------------------------------------
-  float* GF = k.dual ? k.g_feat_dot : k.g_feat;
+  // ---- feature gradient of the slice (native order: coalesced stores) -------------------------------------------
+  float* GF = dual ? k.g_feat_dot : k.g_feat;
   if (GF) {
     float* out = GF + fbase;
-    const int span = e_hi - e_lo;
     for (int idx = tid; idx < n * span; idx += HEAD_THREADS) {
-      const int i = idx / span, e = e_lo + idx - i * span;
+      const int i = idx / span, j = idx - i * span, e = e_lo + j;
       float acc = 0.f;
       for (int w = 0; w < ways; ++w) {
-        if (k.dual) {
-          acc = fmaf(gld[i * ways + w], Wn[w * D + e], acc);
-          acc = fmaf(gl[i * ways + w], Wdn[w * D + e], acc);
+        if (dual) {
+          acc = fmaf(gld[i * ways + w], Wn[w * ld + j], acc);
+          acc = fmaf(gl[i * ways + w], Wdn[w * ld + j], acc);
         } else {
-          acc = fmaf(gl[i * ways + w], Wn[w * D + e], acc);
+          acc = fmaf(gl[i * ways + w], Wn[w * ld + j], acc);
         }
       }
       if (k.mode == 0) {
@@ -467,14 +488,27 @@ extern "C" int xm_head(const XmHeadArgs* a, void* stream_) {
   k.out_w = a->out_w; k.out_b = a->out_b; k.out_stride = a->out_task_stride;
   k.base_w = a->base_w; k.base_b = a->base_b; k.base_stride = a->base_task_stride;
   k.scale = a->scale;
-  const size_t smem = ((size_t)5 * a->n * a->ways + 2 * a->n + (size_t)(a->dual ? 2 : 1) * a->ways * k.D) * 4;
-  XM_REQUIRE(smem <= 200 * 1024, "xm_head: n*ways + ways*D too large for shared memory");
+  // one cluster per task: G CTAs, each owning ~D/G features (at least 16 each, at most 8 CTAs)
+  int G = k.D / 16;
+  if (G > 8) G = 8;
+  if (G < 1) G = 1;
+  const int span_max = (k.D + G - 1) / G + 1, ld = span_max | 1;
+  const bool have_xd = a->dual && a->feat_dot;
+  const size_t smem = ((size_t)7 * a->n * a->ways + 2 * a->n + (size_t)(have_xd ? 2 : 1) * a->n * ld +
+                       (size_t)(a->dual ? 2 : 1) * a->ways * ld) * 4;
+  XM_REQUIRE(smem <= 200 * 1024, "xm_head: n * (ways + D/8) too large for shared memory");
   XM_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  int parts = (num_sms() + a->tasks - 1) / a->tasks;       // CTAs per task: fill the GPU, at most 8
-  if (parts > 8) parts = 8;
-  if (parts > k.D) parts = k.D;
-  if (parts < 1) parts = 1;
-  head_kernel<<<dim3(a->tasks, parts), HEAD_THREADS, smem, stream>>>(k);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a->tasks * G));
+  cfg.blockDim = dim3(HEAD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XM_CUDA(cudaLaunchKernelEx(&cfg, head_kernel, k, G));
   return launched("xm_head");
 }
 

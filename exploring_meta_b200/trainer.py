@@ -88,7 +88,9 @@ class _TrainerBase:
                                             self.step_dev.data_ptr(), stream), 'xm_finish_shard')
         local = self.flat
         if self.world > 1 and self.comm is None:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.red.copy_(self.flat)
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM)
+            local = self.red
         a = _lib.XmAdamArgs()
         a.theta, a.m, a.v, a.n_params = _p(theta_all), _p(self.m), _p(self.v), n
         a.local, a.reduced, a.n_total = _p(local), _p(self.red), self.flat.numel()

@@ -1,7 +1,14 @@
 """Hardware twin of test_multirank_gloo.py: 2 ranks on 2 GPUs of one box (one process per GPU), the meta-batch sharded
 over the ranks, shard sums combined inside the Adam kernel over NVLink peer memory (csrc/comm.cu; also through NCCL for
-comparison).  After two meta-iterations every rank must hold bit-identical parameters, equal to what ONE GPU computes
-for the whole meta-batch up to fp32 reassociation of the task sum (~1e-6 rel).
+comparison).  Checked after two meta-iterations:
+  * the transport is exact: on every rank the reduced buffer equals, bit for bit, rank 0's contribution + rank 1's
+    (fp32, rank order), and the replicas' parameters / Adam moments / BN running statistics are bit-identical;
+  * against ONE GPU running the whole meta-batch: the summed meta-gradient of the first iteration agrees to fp32
+    reassociation.  A task's gradient is not bit-identical between a 16-task and a 32-task launch program (the
+    persistent wgrad / statistics grids partition the work differently, so fp32 partial sums associate differently,
+    ~1e-7 per task) and Adam's first updates are lr * g / (|g| + eps): parameters whose gradient is itself rounding
+    noise move by a different fraction of lr.  The bound on theta is therefore stated as a fraction of the Adam step
+    (|d theta| <= 0.05 * outer_lr * iterations), the bound on the gradient as rel-L2 <= 1e-5.
 Needs >= 2 GPUs: skipped on a single-GPU box (run with ``gpurun --gpus 2``)."""
 import os
 import socket
@@ -34,15 +41,20 @@ def _train(kind, lo, hi, device, iterations=2):
     spec, tasks, shots, steps, lr, shape, seed = _case(kind)
     tr = MamlTrainer(spec, hi - lo, shots, steps, lr, 0.003, device=device, use_graph=True)
     tr.theta.copy_(pspec.init_flat_params(spec, seed=42))
+    grad1 = None
     for it in range(iterations):
         X, Y = make_tasks(tasks, spec.ways, shots, shape, seed=seed + it)
         tr.meta_step(X[lo:hi].to(device), Y[lo:hi].to(device))
+        if it == 0:
+            grad1 = tr.red[:tr.engine.P].cpu().clone()          # summed meta-gradient of the first iteration
     torch.cuda.synchronize(device)
     if tr.comm is not None:
         tr.comm.check()
     loss, acc = tr.metrics()
     stats = torch.cat([torch.cat(tr.running_mean), torch.cat(tr.running_var)]).cpu()
-    return tr.theta.cpu().clone(), float(loss), float(acc), stats
+    return {'theta': tr.theta.cpu().clone(), 'loss': float(loss), 'acc': float(acc), 'stats': stats,
+            'flat': tr.flat.cpu().clone(), 'red': tr.red.cpu().clone(), 'm': tr.m.cpu().clone(),
+            'grad1': grad1}
 
 
 def _worker(rank, world, port, kind, transport, out):
@@ -73,13 +85,20 @@ def test_two_gpus_equal_one_gpu(kind, transport):
             p.join(timeout=300)
             assert p.exitcode == 0
         results = dict(out)
-    ref_theta, ref_loss, ref_acc, ref_stats = _train(kind, 0, _case(kind)[1], torch.device('cuda', 0))
-    (t0, l0, a0, s0), (t1, l1, a1, s1) = results[0], results[1]
-    assert torch.equal(t0, t1), 'replicas diverged'                      # replicated Adam on identical sums
-    assert torch.equal(s0, s1)
-    d = float((t0 - ref_theta).abs().max() / ref_theta.abs().max())
-    print('%s/%s: max |theta_2gpu - theta_1gpu| / max|theta| = %.2e' % (kind, transport, d))
-    assert d <= 1e-6
-    assert torch.allclose(s0, ref_stats, rtol=1e-5, atol=1e-6)
-    assert l0 == pytest.approx(ref_loss, rel=1e-5) and l1 == pytest.approx(ref_loss, rel=1e-5)
-    assert a0 == pytest.approx(ref_acc, abs=1e-6)
+    ref = _train(kind, 0, _case(kind)[1], torch.device('cuda', 0))
+    r0, r1 = results[0], results[1]
+    # transport: exact
+    assert torch.equal(r0['red'], r0['flat'] + r1['flat']) and torch.equal(r1['red'], r0['red'])
+    for key in ('theta', 'm', 'stats'):
+        assert torch.equal(r0[key], r1[key]), 'replicas diverged in %s' % key
+    # against one GPU on the whole meta-batch
+    from oracle import maml_oracle as mo
+    dg = mo.rel_l2(r0['grad1'], ref['grad1'])
+    dth = float((r0['theta'] - ref['theta']).abs().max())
+    print('%s/%s: meta-grad rel-L2 (2 GPUs vs 1) %.2e, max |d theta| %.2e = %.3f Adam steps'
+          % (kind, transport, dg, dth, dth / 0.003))
+    assert dg <= 1e-5
+    assert dth <= 0.05 * 0.003 * 2
+    assert torch.allclose(r0['stats'], ref['stats'], rtol=1e-5, atol=1e-6)
+    assert r0['loss'] == pytest.approx(ref['loss'], rel=1e-5) and r1['loss'] == pytest.approx(ref['loss'], rel=1e-5)
+    assert r0['acc'] == pytest.approx(ref['acc'], abs=1e-6)
