@@ -113,6 +113,29 @@ class XmAdamArgs(Structure):
                 ('step', c_void_p)]
 
 
+class XmRlAdvArgs(Structure):
+    _fields_ = [('replays', c_int32), ('n', c_int32), ('state_dim', c_int32),
+                ('gamma', c_double), ('tau', c_double), ('reg', c_double), ('coef_scale', c_double),
+                ('states', c_void_p), ('next_states', c_void_p), ('rewards', c_void_p), ('dones', c_void_p),
+                ('coef', c_void_p), ('returns', c_void_p)]
+
+
+class XmRlSweepArgs(Structure):
+    _fields_ = [('tasks', c_int32), ('n', c_int32), ('in_dim', c_int32), ('out_dim', c_int32), ('h1', c_int32),
+                ('h2', c_int32), ('activation', c_int32), ('loss', c_int32), ('what', c_int32),
+                ('states', c_void_p), ('actions', c_void_p), ('coef', c_void_p),
+                ('mu_old', c_void_p), ('logstd_old', c_void_p), ('kl_scale', c_float),
+                ('theta', c_void_p), ('theta_task_stride', c_int64),
+                ('theta_dot', c_void_p), ('theta_dot_task_stride', c_int64),
+                ('out', c_void_p), ('out_task_stride', c_int64),
+                ('base', c_void_p), ('base_task_stride', c_int64), ('scale', c_float),
+                ('task_loss', c_void_p), ('task_kl', c_void_p), ('mu_out', c_void_p),
+                ('partial', c_void_p), ('partial_bytes', c_int64)]
+
+
+XM_RL_A2C, XM_RL_SURROGATE, XM_RL_FISHER = 0, 1, 2
+XM_RL_FORWARD, XM_RL_GRAD, XM_RL_HVP = 0, 1, 2
+XM_ACT_RELU, XM_ACT_TANH = 0, 1
 XM_COMM_MAX_WORLD, XM_IPC_HANDLE_BYTES = 8, 64
 
 # name -> (restype, argtypes): every symbol include/xmeta.h declares.
@@ -147,6 +170,9 @@ SYMBOLS = {
     'xm_comm_destroy': (c_int32, [c_void_p]),
     'xm_allreduce_adam': (c_int32, [c_void_p, POINTER(XmAdamArgs), c_void_p]),
     'xm_finish_shard': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    'xm_rl_advantages': (c_int32, [POINTER(XmRlAdvArgs), c_void_p]),
+    'xm_rl_sweep_scratch_bytes': (c_int64, [POINTER(XmRlSweepArgs)]),
+    'xm_rl_sweep': (c_int32, [POINTER(XmRlSweepArgs), c_void_p]),
     'xm_bn_ema': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int32,
                             c_float, c_void_p]),
     'xm_set_precision': (c_int32, [c_int32]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libxmeta.so')
-SOURCES = ['misc.cu', 'conv.cu', 'conv_img.cu', 'img_block.cu', 'img_flat.cu', 'conv_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'bn.cu', 'head.cu', 'sampler.cu', 'comm.cu']
+SOURCES = ['misc.cu', 'conv.cu', 'conv_img.cu', 'img_block.cu', 'img_flat.cu', 'conv_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'bn.cu', 'head.cu', 'sampler.cu', 'comm.cu', 'rl.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

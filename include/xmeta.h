@@ -299,6 +299,61 @@ int xm_allreduce_adam(XmComm* comm, const XmAdamArgs* a, void* stream);
 int xm_finish_shard(const float* loss, const int32_t* correct, int32_t tasks, float* out2, int32_t* step,
                     void* stream);
 
+/* ---- config 5: MAML-TRPO policy-MLP path (ABI item 8) ---------------------------------------
+ * Policy = core_functions/policies.py:30-56 DiagNormalPolicy with two hidden layers: mean(s) = W3 act(W2 act(W1 s +
+ * b1) + b2) + b3, log-std = clamp(sigma, min=log 1e-6), log_prob = MEAN over action dims of the Normal log-density.
+ * Flat parameter vector in DiagNormalPolicy.parameters() order: sigma[out], W1[h1][in], b1[h1], W2[h2][h1], b2[h2],
+ * W3[out][h2], b3[out] (10,604 floats for 2 -> 100 -> 100 -> 2).  Replays are [tasks][n][dim] fp32, n transitions.
+ *
+ * xm_rl_advantages: per replay, everything core_functions/rl.py:95-110 + cherry compute from the replay alone --
+ * discounted returns (ch.td.discount), LinearValue ridge fit on [s, s^2, t, t^2, t^3, 1] and its values, bootstraps,
+ * GAE (ch.pg.generalized_advantage), ch.normalize -- and writes coef[n] = coef_scale * normalised advantage (the
+ * per-sample weight of the policy losses: -1/n for a2c.policy_loss :358, -1/(n*tasks) for the surrogate :469).
+ * Independent of the policy: computed once per meta-optimisation instead of once per loss evaluation.  Reverse scans
+ * run sequentially inside an episode (the reference's order) with one thread per episode; sums in double. */
+typedef struct XmRlAdvArgs {
+  int32_t replays, n, state_dim;
+  double gamma, tau, reg, coef_scale;
+  const float* states; const float* next_states;     /* [replays][n][state_dim] */
+  const float* rewards; const float* dones;          /* [replays][n]            */
+  float* coef;                                       /* [replays][n]            */
+  float* returns;                                    /* optional [replays][n] discounted returns */
+} XmRlAdvArgs;
+int xm_rl_advantages(const XmRlAdvArgs* a, void* stream);
+
+/* xm_rl_sweep: one pass of every task's policy over its n transitions, per-task parameters (theta + t*stride).
+ *   loss XM_RL_A2C       l = sum_n coef[n] * log_prob(a_n | s_n)                     (trpo_a2c_loss, rl.py:346-358)
+ *        XM_RL_SURROGATE l = sum_n coef[n] * exp(log_prob_new - log_prob_old),  kl = mean KL(new || old)/tasks_total
+ *                        with the old policy given by its means mu_old[n][out] and log-std (rl.py:459-469)
+ *        XM_RL_FISHER    the Gauss-Newton factor of that KL at new == old: the output cotangent is
+ *                        F * (tangent of the outputs in direction theta_dot), F = diag(1/sigma_old^2, 2) * kl_scale
+ *   what XM_RL_FORWARD   values only (task_loss / task_kl, optional mu_out): the line search of rl.py:429-438
+ *        XM_RL_GRAD      d l / d theta                          (theta_dot: only for XM_RL_FISHER, where it is required)
+ *        XM_RL_HVP       d/d eps [ d l / d theta ](theta + eps * theta_dot)   (XM_RL_A2C only): the Hessian-vector
+ *                        product of the inner loss = what create_graph=True back-propagates through (rl.py:368-374)
+ * Result r [P] per task through the axpy epilogue out = (base ? base : 0) + scale * r  (maml_update fused:
+ * theta' = theta - inner_lr * grad; cotangent recursion v - inner_lr * H v).  Deterministic: per-CTA partial sums in
+ * `partial` (xm_rl_sweep_scratch_bytes), reduced in a fixed order. */
+enum { XM_RL_A2C = 0, XM_RL_SURROGATE = 1, XM_RL_FISHER = 2 };
+enum { XM_RL_FORWARD = 0, XM_RL_GRAD = 1, XM_RL_HVP = 2 };
+enum { XM_ACT_RELU = 0, XM_ACT_TANH = 1 };
+typedef struct XmRlSweepArgs {
+  int32_t tasks, n, in_dim, out_dim, h1, h2, activation, loss, what;
+  const float* states; const float* actions;                  /* [tasks][n][in_dim], [tasks][n][out_dim] */
+  const float* coef;                                          /* [tasks][n] (unused by XM_RL_FISHER)     */
+  const float* mu_old; const float* logstd_old;               /* [tasks][n][out_dim], [tasks][out_dim]   */
+  float kl_scale;                                             /* 1 / (n * out_dim * tasks_total)         */
+  const float* theta; int64_t theta_task_stride;
+  const float* theta_dot; int64_t theta_dot_task_stride;
+  float* out; int64_t out_task_stride;
+  const float* base; int64_t base_task_stride; float scale;
+  float* task_loss; float* task_kl;                           /* optional [tasks]                        */
+  float* mu_out;                                              /* optional [tasks][n][out_dim]            */
+  float* partial; int64_t partial_bytes;
+} XmRlSweepArgs;
+int64_t xm_rl_sweep_scratch_bytes(const XmRlSweepArgs* a);
+int xm_rl_sweep(const XmRlSweepArgs* a, void* stream);
+
 /* BatchNorm running-statistics side effect, composed sequentially like the reference's shared
  * buffers see it: for o in [0,n_outer) for i in [0,n_inner): r <- (1-m) r + m s(o,i), where
  * s(o,i) = {mean[C], unbiased var[C]} at call_stats + o*outer_stride + i*inner_stride (floats). */

@@ -653,6 +653,119 @@ class EmulatedLib:
         return self.xm_adam_step(a.theta, a.reduced, a.m, a.v, a.n_params, a.grad_scale, a.lr, a.beta1, a.beta2,
                                  a.eps, step, stream)
 
+    # ------------------------------------------------------------------ config 5: policy-MLP path
+    def xm_rl_advantages(self, ref, stream):
+        """Contract of csrc/rl.cu::rl_adv_kernel in float64 torch ops (cherry's algorithms, SURVEY App. A.2)."""
+        self.launches += 1
+        a = self._args(ref)
+        n, sd = a.n, a.state_dim
+        for rp in range(a.replays):
+            s = view(a.states + 4 * rp * n * sd, (n, sd)).double()
+            ns = view(a.next_states + 4 * rp * n * sd, (n, sd)).double()
+            r = view(a.rewards + 4 * rp * n, (n,)).double()
+            d = view(a.dones + 4 * rp * n, (n,)).double()
+
+            def scan(factor, x):
+                out, R = torch.zeros_like(x), 0.0
+                for t in reversed(range(n)):
+                    R = x[t] + factor * (R * (1.0 - d[t]))
+                    out[t] = R
+                return out
+
+            def feats(st):
+                t = torch.arange(n, dtype=torch.float64) / 100.0
+                return torch.cat([st, st ** 2, t[:, None], t[:, None] ** 2, t[:, None] ** 3,
+                                  torch.ones(n, 1, dtype=torch.float64)], dim=1)
+            ret = scan(a.gamma, r)
+            f = feats(s)
+            A = f.t() @ f + a.reg * torch.eye(f.size(1), dtype=torch.float64)
+            coef = torch.linalg.solve(A, f.t() @ ret)
+            v, nv = f @ coef, feats(ns) @ coef
+            boot = v * (1 - d) + nv * d
+            nxt = torch.cat([boot[1:], torch.zeros(1, dtype=torch.float64)])
+            td = r + a.gamma * (1 - d) * nxt - boot
+            adv = scan(a.tau * a.gamma, td)
+            if n > 1:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            view(a.coef + 4 * rp * n, (n,)).copy_((a.coef_scale * adv).float())
+            if a.returns:
+                view(a.returns + 4 * rp * n, (n,)).copy_(ret.float())
+        return 0
+
+    def xm_rl_sweep_scratch_bytes(self, ref):
+        return 64
+
+    def xm_rl_sweep(self, ref, stream):
+        """Contract of csrc/rl.cu::rl_sweep_kernel, evaluated with torch.autograd in float64 (double backward for the
+        Hessian-vector product, jvp / vjp for the Fisher factor) -- independent of the kernel's hand-derived tangents."""
+        import math
+        self.launches += 1
+        a = self._args(ref)
+        n, IN, OUT, H1, H2 = a.n, a.in_dim, a.out_dim, a.h1, a.h2
+        P = OUT + H1 * IN + H1 + H2 * H1 + H2 + OUT * H2 + OUT
+        actf = torch.tanh if a.activation == 1 else torch.relu
+        LOG_EPS = math.log(1e-6)
+
+        def unpack(th):
+            o, parts = 0, []
+            for shape in ((OUT,), (H1, IN), (H1,), (H2, H1), (H2,), (OUT, H2), (OUT,)):
+                k = 1
+                for d in shape:
+                    k *= d
+                parts.append(th[o:o + k].view(*shape))
+                o += k
+            return parts
+
+        def outputs(th, x):
+            sg, W1, b1, W2, b2, W3, b3 = unpack(th)
+            h = actf(x @ W1.t() + b1)
+            h = actf(h @ W2.t() + b2)
+            return h @ W3.t() + b3, torch.clamp(sg, min=LOG_EPS)
+
+        for t in range(a.tasks):
+            x = view(a.states + 4 * t * n * IN, (n, IN)).double()
+            th0 = view(a.theta + 4 * t * a.theta_task_stride, (P,)).double().clone()
+            act = view(a.actions + 4 * t * n * OUT, (n, OUT)).double() if a.actions else None
+            coef = view(a.coef + 4 * t * n, (n,)).double() if a.coef else None
+            thd = view(a.theta_dot + 4 * t * a.theta_dot_task_stride, (P,)).double().clone() if a.theta_dot else None
+            lamo = view(a.logstd_old + 4 * t * OUT, (OUT,)).double() if a.logstd_old else None
+            muo = view(a.mu_old + 4 * t * n * OUT, (n, OUT)).double() if a.mu_old else None
+
+            def log_prob(mu, lam, actions):
+                return (-(actions - mu) ** 2 / (2 * torch.exp(2 * lam)) - lam - 0.5 * math.log(2 * math.pi)).mean(dim=1)
+
+            def loss_fn(th):
+                mu, lam = outputs(th, x)
+                if a.loss == 0:
+                    return (coef * log_prob(mu, lam, act)).sum(), torch.zeros((), dtype=torch.float64)
+                lp, lpo = log_prob(mu, lam, act), log_prob(muo, lamo, act)
+                kl = (lamo - lam + (torch.exp(2 * lam) + (mu - muo) ** 2) / (2 * torch.exp(2 * lamo)) - 0.5).sum()
+                return (coef * torch.exp(lp - lpo)).sum(), a.kl_scale * kl
+
+            res, l, kl = None, None, None
+            if a.loss == 2:                                         # Fisher factor J^T F J theta_dot
+                (mu, lam), (mud, lamd) = torch.autograd.functional.jvp(lambda th: outputs(th, x), th0, thd)
+                cot = (a.kl_scale * mud * torch.exp(-2 * lamo), a.kl_scale * 2.0 * n * lamd)
+                _o, res = torch.autograd.functional.vjp(lambda th: outputs(th, x), th0, cot)
+            else:
+                th = th0.requires_grad_()
+                l, kl = loss_fn(th)
+                if a.what == 1:
+                    res = torch.autograd.grad(l, th)[0]
+                elif a.what == 2:
+                    g = torch.autograd.grad(l, th, create_graph=True)[0]
+                    res = torch.autograd.grad((g * thd).sum(), th)[0]
+                if a.mu_out:
+                    view(a.mu_out + 4 * t * n * OUT, (n, OUT)).copy_(outputs(th0.detach(), x)[0].float())
+            if res is not None:
+                base = view(a.base + 4 * t * a.base_task_stride, (P,)).double() if a.base else torch.zeros(P, dtype=torch.float64)
+                view(a.out + 4 * t * a.out_task_stride, (P,)).copy_((base + a.scale * res).float())
+            if a.task_loss and l is not None:
+                view(a.task_loss + 4 * t, (1,))[0] = float(l)
+            if a.task_kl and kl is not None:
+                view(a.task_kl + 4 * t, (1,))[0] = float(kl)
+        return 0
+
     def xm_bn_ema(self, rm, rv, stats, n_outer, outer_stride, n_inner, inner_stride, C, momentum, stream):
         self.launches += 1
         m, v = view(rm, (C,)), view(rv, (C,))

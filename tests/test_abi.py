@@ -48,7 +48,8 @@ def test_struct_layout_matches_c(tmp_path):
     """sizeof/offsetof of every argument block as the C compiler sees them == the ctypes mirror."""
     structs = {'XmBlockGeom': _lib.XmBlockGeom, 'XmConvArgs': _lib.XmConvArgs, 'XmWgradArgs': _lib.XmWgradArgs,
                'XmBnArgs': _lib.XmBnArgs, 'XmImgArgs': _lib.XmImgArgs, 'XmHeadArgs': _lib.XmHeadArgs,
-               'XmAnilHeadArgs': _lib.XmAnilHeadArgs, 'XmSampleArgs': _lib.XmSampleArgs}
+               'XmAnilHeadArgs': _lib.XmAnilHeadArgs, 'XmSampleArgs': _lib.XmSampleArgs,
+               'XmAdamArgs': _lib.XmAdamArgs, 'XmRlAdvArgs': _lib.XmRlAdvArgs, 'XmRlSweepArgs': _lib.XmRlSweepArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "xmeta.h"', 'int main(void){']
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -3,12 +3,14 @@ over the ranks, shard sums combined inside the Adam kernel over NVLink peer memo
 comparison).  Checked after two meta-iterations:
   * the transport is exact: on every rank the reduced buffer equals, bit for bit, rank 0's contribution + rank 1's
     (fp32, rank order), and the replicas' parameters / Adam moments / BN running statistics are bit-identical;
-  * against ONE GPU running the whole meta-batch: the summed meta-gradient of the first iteration agrees to fp32
-    reassociation.  A task's gradient is not bit-identical between a 16-task and a 32-task launch program (the
-    persistent wgrad / statistics grids partition the work differently, so fp32 partial sums associate differently,
-    ~1e-7 per task) and Adam's first updates are lr * g / (|g| + eps): parameters whose gradient is itself rounding
-    noise move by a different fraction of lr.  The bound on theta is therefore stated as a fraction of the Adam step
-    (|d theta| <= 0.05 * outer_lr * iterations), the bound on the gradient as rel-L2 <= 1e-5.
+  * the distributed step equals ONE GPU running the two shards one after the other with the same shard-sized launch
+    programs, summing in rank order and stepping Adam once: meta-gradient to <= 1e-6 rel-L2, parameters to a
+    hundredth of an Adam step;
+  * against ONE GPU running the whole meta-batch as a single launch program: loss / accuracy / BN statistics agree;
+    the meta-gradient agrees up to the batching sensitivity documented in DESIGN section 5 -- a task's gradient is not
+    bit-identical between a 16-task and a 32-task program (persistent grids partition the work differently, fp32
+    partial sums associate differently, ~1e-7 per task) and that last bit can flip a ReLU / max-pool decision
+    (1e-3-level change of that task's gradient; the reference's own fp32 run does the same between thread counts).
 Needs >= 2 GPUs: skipped on a single-GPU box (run with ``gpurun --gpus 2``)."""
 import os
 import socket
@@ -57,6 +59,36 @@ def _train(kind, lo, hi, device, iterations=2):
             'grad1': grad1}
 
 
+def _train_shards_on_one_gpu(kind, world, device, iterations=2):
+    """What the ``world`` ranks compute, on one GPU: shard-sized programs run one after the other, shard sums added in
+    rank order, one Adam step on the sum."""
+    from exploring_meta_b200 import spec as pspec
+    from exploring_meta_b200.synthetic import make_tasks
+    from exploring_meta_b200.trainer import MamlTrainer
+    spec, tasks, shots, steps, lr, shape, seed = _case(kind)
+    per = tasks // world
+    tr = MamlTrainer(spec, per, shots, steps, lr, 0.003, device=device, use_graph=False)
+    tr.theta.copy_(pspec.init_flat_params(spec, seed=42))
+    e, P = tr.engine, tr.engine.P
+    grad1 = None
+    for it in range(iterations):
+        X, Y = make_tasks(tasks, spec.ways, shots, shape, seed=seed + it)
+        parts = []
+        for r in range(world):
+            e.x.copy_(X[r * per:(r + 1) * per]); e.y.copy_(Y[r * per:(r + 1) * per])
+            e.prog.replay(torch.cuda.current_stream(device).cuda_stream)
+            parts.append(tr.flat[:P].clone())
+        total = parts[0]
+        for q in parts[1:]:
+            total = total + q
+        tr.flat[:P].copy_(total)
+        if it == 0:
+            grad1 = total.cpu().clone()
+        tr._reduce_and_step(tr.theta, tasks)
+    torch.cuda.synchronize(device)
+    return {'theta': tr.theta.cpu().clone(), 'grad1': grad1}
+
+
 def _worker(rank, world, port, kind, transport, out):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       XM_COMM=transport)
@@ -91,14 +123,20 @@ def test_two_gpus_equal_one_gpu(kind, transport):
     assert torch.equal(r0['red'], r0['flat'] + r1['flat']) and torch.equal(r1['red'], r0['red'])
     for key in ('theta', 'm', 'stats'):
         assert torch.equal(r0[key], r1[key]), 'replicas diverged in %s' % key
-    # against one GPU on the whole meta-batch
     from oracle import maml_oracle as mo
+    # the same computation on one GPU, shard by shard
+    seq = _train_shards_on_one_gpu(kind, 2, torch.device('cuda', 0))
+    dgs = mo.rel_l2(r0['grad1'], seq['grad1'])
+    dts = float((r0['theta'] - seq['theta']).abs().max())
+    # one GPU, the whole meta-batch as one launch program
     dg = mo.rel_l2(r0['grad1'], ref['grad1'])
     dth = float((r0['theta'] - ref['theta']).abs().max())
-    print('%s/%s: meta-grad rel-L2 (2 GPUs vs 1) %.2e, max |d theta| %.2e = %.3f Adam steps'
-          % (kind, transport, dg, dth, dth / 0.003))
-    assert dg <= 1e-5
-    assert dth <= 0.05 * 0.003 * 2
+    print('%s/%s: vs shard-by-shard on one GPU: meta-grad rel-L2 %.2e, max |d theta| %.2e (%.4f Adam steps); '
+          'vs one %d-task program: meta-grad rel-L2 %.2e, max |d theta| %.2e (%.3f Adam steps)'
+          % (kind, transport, dgs, dts, dts / 0.003, _case(kind)[1], dg, dth, dth / 0.003))
+    assert dgs <= 1e-6
+    assert dts <= 0.01 * 0.003 * 2
+    assert dg <= 2e-2                       # batching sensitivity (a flipped decision), not the transport
     assert torch.allclose(r0['stats'], ref['stats'], rtol=1e-5, atol=1e-6)
     assert r0['loss'] == pytest.approx(ref['loss'], rel=1e-5) and r1['loss'] == pytest.approx(ref['loss'], rel=1e-5)
     assert r0['acc'] == pytest.approx(ref['acc'], abs=1e-6)

@@ -1,0 +1,115 @@
+"""Config 5 (MAML-TRPO policy MLP): the product's launch sequences (exploring_meta_b200/rl_engine.py) against the
+oracle (oracle/rl_oracle.py, float64) and the golden fixture generated from the reference's own rl.py / policies.py
+(tests/golden/rl/rl_trpo_small.npz).  ``kdev`` runs them on the CPU emulator of the C ABI (``-m "not gpu"``: checks
+the forward-over-reverse algebra, the Gauss-Newton Fisher product, CG and the line search) and on the CUDA kernels
+(``-m gpu``: the parity test proper).
+
+Tolerances (float32 path against the float64 oracle): adapted parameters 1e-5, meta-gradient 1e-4 rel-L2, the
+parameters after one meta-optimisation 1e-4 rel-L2 of the UPDATE (theta1 - theta0), same accepted line-search step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from exploring_meta_b200.rl_engine import TrpoEngine
+from exploring_meta_b200.synthetic import make_replays
+from oracle import cherry_shim as ch
+from oracle import rl_oracle as ro
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'rl', 'rl_trpo_small.npz')
+CFG = {'inner_lr': 0.05, 'tau': 1.0, 'gamma': 0.99, 'value_reg': 2, 'max_kl': 0.01, 'ls_max_steps': 15,
+       'backtrack_factor': 0.5, 'outer_lr': 0.3}
+
+
+def flat(ps):
+    return torch.cat([p.detach().reshape(-1) for p in ps])
+
+
+def rel(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def _engine(tasks, episodes, horizon, seed, dev, activation='tanh'):
+    data32 = make_replays(tasks, episodes, horizon, seed=seed)
+    data64 = make_replays(tasks, episodes, horizon, seed=seed, dtype=torch.float64)
+    e = TrpoEngine(tasks, episodes * horizon, 2, 2, (100, 100), activation, CFG['inner_lr'], CFG['gamma'], CFG['tau'],
+                   CFG['value_reg'], device=dev)
+    e.load_replays(data32)
+    return e, data64
+
+
+def test_advantages_match_cherry_restatement(kdev):
+    e, data = _engine(3, 4, 25, 0, kdev)
+    for t, (sup, qry) in enumerate(data):
+        for k, rep in enumerate((sup, qry)):
+            adv = ch.normalize(ro.compute_advantages(rep, CFG['tau'], CFG['gamma'], CFG['value_reg'])).reshape(-1)
+            scale = -1.0 / e.n if k == 0 else -1.0 / (e.n * e.tasks)
+            assert rel(e.coef[k, t], scale * adv) < 2e-5
+
+
+def test_trpo_update_matches_oracle(kdev):
+    e, data = _engine(3, 4, 25, 0, kdev)
+    theta = ro.init_policy(dtype=torch.float64, seed=42)
+    th32 = flat(theta).float().to(kdev)
+    out = e.adapt(th32)
+    for t, (sup, _q) in enumerate(data):
+        ref = ro.trpo_update([p.clone().requires_grad_() for p in theta], sup, CFG['inner_lr'], CFG['tau'], CFG['gamma'],
+                             CFG['value_reg'], first_order=True)
+        assert rel(out[t], flat(ref)) < 1e-5
+        # the adaptation step itself (theta' - theta = -lr * gradient): 1e-4 of its norm + the fp32 rounding of theta'
+        d, dref = out[t].cpu().double() - flat(theta), flat(ref) - flat(theta)
+        assert float((d - dref).norm()) <= 1e-4 * float(dref.norm()) + 2e-7 * float(flat(theta).norm())
+
+
+@pytest.mark.parametrize('activation', ['tanh', 'relu'])
+def test_meta_gradient_and_fisher_product_match_oracle(kdev, activation):
+    import math
+    act = torch.tanh if activation == 'tanh' else torch.relu
+    e, data = _engine(2, 3, 20, 5, kdev, activation)
+    theta = [p.requires_grad_() for p in ro.init_policy(dtype=torch.float64, seed=3)]
+    theta[0].data += torch.tensor([0.2, -0.3], dtype=torch.float64)          # sigma != 0: exercises the log-std terms
+    saved = ro.policy_mean
+    ro.policy_mean = lambda params, states, activation=act: saved(params, states, activation)
+    try:
+        old = [[x.detach() for x in ro.trpo_update(theta, sup, CFG['inner_lr'], CFG['tau'], CFG['gamma'], CFG['value_reg'],
+                                                   first_order=True)] for sup, _q in data]
+        loss, kl = ro.meta_surrogate_loss(theta, [[s, q] for s, q in data], old, CFG)
+        g_ref = flat(torch.autograd.grad(loss, theta, retain_graph=True))
+        fvp = ch.hessian_vector_product(kl, theta, damping=1e-5)
+        torch.manual_seed(1)
+        v = torch.randn(g_ref.numel(), dtype=torch.float64)
+        hv_ref = fvp(v)
+        # a perturbed point for the line-search quantities (KL > 0 there)
+        cand = [(p.detach() - 0.05 * torch.randn_like(p) * p.detach().abs().mean()).requires_grad_() for p in theta]
+        loss_c, kl_c = ro.meta_surrogate_loss(cand, [[s, q] for s, q in data], old, CFG)
+    finally:
+        ro.policy_mean = saved
+    th32 = flat(theta).float().to(kdev)
+    e.set_old_policies(torch.stack([flat(o) for o in old]).float().to(kdev))
+    l, k, g = e.gradient(th32)
+    assert abs(float(l) - float(loss)) < 1e-5 * max(1.0, abs(float(loss))) and abs(float(k)) < 1e-9
+    assert rel(g, g_ref) < 1e-4
+    hv = e.fvp(th32, v.float().to(kdev))
+    assert rel(hv, hv_ref) < 1e-4
+    lc, kc = e.loss_and_kl(flat(cand).float().to(kdev))
+    assert abs(float(lc) - float(loss_c)) < 2e-5 * max(1.0, abs(float(loss_c)))
+    assert abs(float(kc) - float(kl_c)) < 1e-4 * abs(float(kl_c)) + 1e-9
+
+
+def test_meta_optimize_trpo_matches_reference_fixture(kdev):
+    g = np.load(GOLD)
+    e, _data = _engine(int(g['tasks']), int(g['episodes']), int(g['horizon']), int(g['seed']), kdev)
+    theta0 = torch.from_numpy(g['theta0']).float().to(kdev)
+    old = e.adapt(theta0).clone()                                       # fast_adapt_trpo(first_order=True): rl/maml_trpo.py:107-111
+    assert rel(old, torch.from_numpy(g['old_params'])) < 1e-5
+    e.set_old_policies(old)
+    new, diag = e.meta_optimize(theta0, CFG['max_kl'], CFG['ls_max_steps'], CFG['backtrack_factor'], CFG['outer_lr'])
+    assert abs(diag['old_loss'] - float(g['old_loss'])) < 1e-5 and abs(diag['old_kl']) < 1e-9
+    assert rel(diag['grad'], torch.from_numpy(g['grad'])) < 1e-4
+    assert rel(diag['step'], torch.from_numpy(g['step'])) < 2e-3        # 10 CG iterations on a damped 1e-5 system
+    assert diag['ls_step'] == int(g['ls_step'])
+    upd_ref = torch.from_numpy(g['theta1'] - g['theta0'])
+    assert rel(new.cpu().double() - torch.from_numpy(g['theta0']), upd_ref) < 2e-3
+    assert rel(new, torch.from_numpy(g['theta1'])) < 1e-4
