@@ -47,6 +47,13 @@ CONFIGS = {
                      '(synthetic 28x28x1)'),
 }
 IN_SHAPE = {'omni': (1, 28, 28), 'min': (3, 84, 84)}
+# BASELINE.json configs[4]: MAML-TRPO policy MLP on synthetic Particles2D-style replays
+RL = dict(tasks=40, episodes=20, horizon=100, inner_lr=0.001, gamma=0.99, tau=1.0, value_reg=2, max_kl=0.01,
+          ls_max_steps=15, backtrack_factor=0.5, outer_lr=1.0,
+          metric='meta-train tasks/sec (MAML-TRPO policy MLP)',
+          workload='MAML-TRPO 2x100 tanh policy MLP, 40 tasks x (support + query replay of 20 episodes x 100 steps), '
+                   'one first-order adaptation per task + one meta_optimize_trpo (second-order gradient, 10 CG '
+                   'iterations of Fisher-vector products, line search) per step; synthetic Particles2D-style replays')
 
 
 def parse():
@@ -55,7 +62,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS) + [5])
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--tasks', type=int, default=0, help='tasks per GPU (default: from --config and --scaling)')
     ap.add_argument('--inner-steps', type=int, default=0, help='override the config\'s inner steps')
@@ -556,9 +563,133 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def rl_cpu_rate(tasks, reps, threads=None):
+    """Oracle port of rl/maml_trpo.py:101-134 (first-order adaptation per task + meta_optimize_trpo) on ``tasks``
+    tasks, fp32, all host cores; tasks/s."""
+    import torch
+    from oracle import rl_oracle as ro
+    from exploring_meta_b200.synthetic import make_replays
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = {k: RL[k] for k in ('inner_lr', 'tau', 'gamma', 'value_reg', 'max_kl', 'ls_max_steps', 'backtrack_factor', 'outer_lr')}
+    theta = ro.init_policy(seed=42)
+    data = make_replays(tasks, RL['episodes'], RL['horizon'], seed=0)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        old = [[x.detach() for x in ro.trpo_update([p.clone().requires_grad_() for p in theta], sup, cfg['inner_lr'],
+                                                   cfg['tau'], cfg['gamma'], cfg['value_reg'], first_order=True)]
+               for sup, _q in data]
+        ro.meta_optimize_trpo(theta, [[s_, q_] for s_, q_ in data], old, cfg)
+        times.append(time.perf_counter() - t0)
+    return tasks / (sum(times) / len(times)), cores, times
+
+
+def rl_config(args):
+    return {'workload': RL['workload'], 'baseline_config': 5, 'global_meta_batch': RL['tasks'],
+            'transitions_per_replay': RL['episodes'] * RL['horizon'], 'inner_lr': RL['inner_lr'], 'max_kl': RL['max_kl']}
+
+
+def run_rl_reference(args):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    sample = 4
+    rate, cores, times = rl_cpu_rate(sample, max(1, min(args.steps, 3)))
+    desc = '%d-task sample of the 40-task meta-batch per step, fp32, %d torch threads, oracle port' % (sample, cores)
+    print(json.dumps({'impl': 'reference', 'metric': RL['metric'], 'value': rate, 'unit': 'tasks/s', 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * sum(times) / len(times),
+                      'higher_is_better': True, 'scaling': 'replicas only', 'vs_baseline': None, 'dtype': 'f32',
+                      'data': 'synthetic', 'config': rl_config(args),
+                      'cpu_baseline': {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+                      'e2e': {'value': rate, 'unit': 'tasks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                      'gpu_launches': 0}), flush=True)
+
+
+def run_rl(args):
+    """Config 5 on one GPU (the path does not shard in the reference's configuration: N > 1 = replicas only)."""
+    import torch
+    from exploring_meta_b200 import _lib
+    from exploring_meta_b200.rl_engine import TrpoEngine
+    from exploring_meta_b200.synthetic import make_replays
+    from oracle import rl_oracle as ro
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, n = RL['tasks'], RL['episodes'] * RL['horizon']
+    e = TrpoEngine(B, n, 2, 2, (100, 100), 'tanh', RL['inner_lr'], RL['gamma'], RL['tau'], RL['value_reg'], device=dev)
+    theta = torch.cat([p.reshape(-1) for p in ro.init_policy(seed=42)]).to(dev)
+    host = []
+    for b in range(2):
+        data = make_replays(B, RL['episodes'], RL['horizon'], seed=b)
+        host.append({k: [torch.stack([t[j][k].reshape(n, -1) for t in data]).pin_memory() for j in range(2)]
+                     for k in ('states', 'actions', 'rewards', 'dones', 'next_states')})
+    fields = {'states': e.states, 'actions': e.actions, 'rewards': e.rewards, 'dones': e.dones, 'next_states': e.next_states}
+
+    def stage(batch):
+        for k, dst in fields.items():
+            for j in range(2):
+                dst[j].copy_(batch[k][j].view_as(dst[j]), non_blocking=True)
+
+    def step(th):
+        e.prepare()                                           # advantages of all 80 replays
+        old = e.adapt(th).clone()                             # fast_adapt_trpo(first_order=True) for every task
+        e.set_old_policies(old)
+        new, diag = e.meta_optimize(th, RL['max_kl'], RL['ls_max_steps'], RL['backtrack_factor'], RL['outer_lr'])
+        return new, diag
+
+    stage(host[0])
+    l0 = int(lib.xm_launch_count())
+    _new, diag = step(theta)
+    torch.cuda.synchronize()
+    launches = int(lib.xm_launch_count()) - l0
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        step(theta)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(theta)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    ev0.record()
+    for i in range(args.steps):
+        stage(host[i % 2])
+        new, d_ = step(theta)
+        new_h = new.cpu()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms2 = ev0.elapsed_time(ev1) / args.steps
+    h2d = sum(t.numel() * 4 for k in host[0] for t in host[0][k])
+    line = {'metric': RL['metric'], 'value': B / (ms / 1e3), 'unit': 'tasks/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'replicas only',
+            'vs_baseline': None, 'dtype': 'f32 (exact fp32 CUDA-core products; advantages in f64)', 'data': 'synthetic',
+            'config': rl_config(args),
+            'run': {'line_search_step': diag['ls_step'], 'l2_policy': 'latency-bound: %d launches of <= 1.7 GFLOP per step; '
+                    'working set (replays 5 MB, per-task vectors 7 MB) is L2-resident by nature of the workload' % launches},
+            'e2e': {'value': B / (ms2 / 1e3), 'unit': 'tasks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': e.P * 4,
+                    'ms_per_step': ms2},
+            'gpu_launches': launches * args.steps, 'clocks': clocks}
+    if not args.no_cpu_baseline:
+        rate, cores, times = rl_cpu_rate(4, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'tasks/s', 'cores': cores, 'kind': 'port',
+                                'sample': '4-task sample x 1 repetition, fp32, %d torch threads (oracle port of '
+                                          'rl/maml_trpo.py:101-134)' % cores}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.config == 5:
+        (run_rl_reference if a.impl == 'reference' else run_rl)(a)
+    elif a.impl == 'reference':
         run_reference(a)
     else:
         run_ours(a)

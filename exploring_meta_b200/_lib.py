@@ -117,7 +117,7 @@ class XmRlAdvArgs(Structure):
     _fields_ = [('replays', c_int32), ('n', c_int32), ('state_dim', c_int32),
                 ('gamma', c_double), ('tau', c_double), ('reg', c_double), ('coef_scale', c_double),
                 ('states', c_void_p), ('next_states', c_void_p), ('rewards', c_void_p), ('dones', c_void_p),
-                ('coef', c_void_p), ('returns', c_void_p)]
+                ('coef', c_void_p), ('returns', c_void_p), ('advantages', c_void_p)]
 
 
 class XmRlSweepArgs(Structure):

@@ -1,0 +1,135 @@
+"""Mirror of the reference's ``core_functions/rl.py`` for the MAML-TRPO path (config 5): same function names,
+argument order and side effects, running on libxmeta's kernels through ``rl_engine.TrpoEngine``.
+
+  compute_advantages   rl.py:95-110     trpo_a2c_loss        rl.py:346-358     trpo_update   rl.py:361-374
+  fast_adapt_trpo      rl.py:377-406    meta_surrogate_loss  rl.py:441-473     meta_optimize_trpo   rl.py:409-438
+
+``episodes`` / replays are anything with cherry's ExperienceReplay accessors (``state() action() reward() done()
+next_state()``) or dicts with the plural keys.  Losses are returned as detached device scalars: the second-order
+information the reference carries in autograd graphs is recomputed inside ``meta_optimize_trpo`` from the stored
+replays (exactly what the reference does: it re-adapts from ``iter_replays``, rl.py:449-454)."""
+import torch
+
+from ..rl_engine import KEYS, LOG_EPS, TrpoEngine
+
+_ACCESSOR = {'states': 'state', 'actions': 'action', 'rewards': 'reward', 'dones': 'done', 'next_states': 'next_state'}
+_engines = {}
+
+
+def get_episode_values(episodes):
+    """rl.py:49-56 (without the device move: tensors are copied into the engine's buffers)."""
+    if isinstance(episodes, dict):
+        return tuple(episodes[k] for k in KEYS)
+    return tuple(getattr(episodes, _ACCESSOR[k])() for k in KEYS)
+
+
+def _as_dict(episodes):
+    return dict(zip(KEYS, get_episode_values(episodes)))
+
+
+def _engine(policy, baseline, tasks, n, inner_lr, gamma, tau, device):
+    key = (tasks, n, policy.input_size, policy.output_size, tuple(policy.hiddens), policy.activation, str(device))
+    e = _engines.get(key)
+    if e is None:
+        e = TrpoEngine(tasks, n, policy.input_size, policy.output_size, tuple(policy.hiddens), policy.activation,
+                       inner_lr, gamma, tau, baseline.reg, device=device)
+        _engines[key] = e
+    e.lr, e.gamma, e.tau, e.reg = float(inner_lr), float(gamma), float(tau), float(baseline.reg)
+    return e
+
+
+def _device_of(policy):
+    return next(policy.parameters()).device
+
+
+def compute_advantages(baseline, tau, gamma, rewards, dones, states, next_states, update_vf=True):
+    """Un-normalised GAE advantages [N, 1] of one replay with the LinearValue baseline fitted to its returns
+    (``update_vf=False`` -- re-using an earlier fit -- is not what the TRPO path does and is not supported)."""
+    if not update_vf:
+        raise NotImplementedError('compute_advantages(update_vf=False)')
+    import ctypes
+    from .. import _lib
+    from ..engine import _p
+    dev = states.device
+    n, sd = states.shape[0], states.shape[1]
+    f = lambda t: t.reshape(n, -1).float().contiguous()                                    # noqa: E731
+    s, ns, r, d = f(states), f(next_states), f(rewards).reshape(n), f(dones).reshape(n)
+    coef, adv = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    a = _lib.XmRlAdvArgs()
+    a.replays, a.n, a.state_dim = 1, n, sd
+    a.gamma, a.tau, a.reg, a.coef_scale = gamma, tau, baseline.reg, 1.0
+    a.states, a.next_states, a.rewards, a.dones = _p(s), _p(ns), _p(r), _p(d)
+    a.coef, a.advantages = _p(coef), _p(adv)
+    stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == 'cuda' else 0
+    _lib.check(_lib.load().xm_rl_advantages(ctypes.byref(a), stream), 'xm_rl_advantages')
+    return adv.view(n, 1)
+
+
+def trpo_a2c_loss(episodes, learner, baseline, gamma, tau, update_vf=True):
+    """-mean(log_prob * normalised advantage) of ``learner`` on ``episodes`` (value only)."""
+    rep = _as_dict(episodes)
+    dev = _device_of(learner)
+    e = _engine(learner, baseline, 1, rep['states'].shape[0], 0.0, gamma, tau, dev)
+    e.load_replays([[rep, rep]])
+    theta = learner.flat_parameters().to(dev)
+    return e.a2c_loss(theta)[0]
+
+
+def trpo_update(episodes, learner, baseline, inner_lr, gamma, tau, anil=False, first_order=False):
+    """One inner step theta' = theta - inner_lr * grad(trpo_a2c_loss) written into ``learner`` (``maml_update`` mutates
+    and returns the module it is given, rl.py:374)."""
+    if anil:
+        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+    rep = _as_dict(episodes)
+    dev = _device_of(learner)
+    e = _engine(learner, baseline, 1, rep['states'].shape[0], inner_lr, gamma, tau, dev)
+    e.load_replays([[rep, rep]])
+    out = e.adapt(learner.flat_parameters().to(dev))
+    return learner.load_flat_parameters(out[0])
+
+
+def fast_adapt_trpo(task, learner, baseline, params, anil=False, first_order=False, render=False):
+    """rl.py:377-406: ``task.run(policy, episodes=...)`` collects the replays (environment side, caller-provided)."""
+    task_replay = []
+    for _step in range(params['adapt_steps']):
+        support_episodes = task.run(learner, episodes=params['adapt_batch_size'], render=render)
+        task_replay.append(support_episodes)
+        learner = trpo_update(support_episodes, learner, baseline, params['inner_lr'], params['gamma'], params['tau'],
+                              anil=anil, first_order=first_order)
+    query_episodes = task.run(learner, episodes=params['adapt_batch_size'])
+    task_replay.append(query_episodes)
+    valid_loss = trpo_a2c_loss(query_episodes, learner, baseline, params['gamma'], params['tau'], update_vf=False)
+    query_rew = get_episode_values(query_episodes)[2].sum().item() / params['adapt_batch_size']
+    return learner, valid_loss, task_replay, query_rew, 0.0
+
+
+def _prepare(iter_replays, iter_policies, policy, baseline, params):
+    if any(len(r) != 2 for r in iter_replays):
+        raise NotImplementedError('one adaptation step (one support replay + the query replay per task)')
+    dev = _device_of(policy)
+    reps = [[_as_dict(s), _as_dict(q)] for s, q in iter_replays]
+    n = reps[0][0]['states'].shape[0]
+    e = _engine(policy, baseline, len(reps), n, params['inner_lr'], params['gamma'], params['tau'], dev)
+    e.load_replays(reps)
+    e.set_old_policies(torch.stack([p.flat_parameters() for p in iter_policies]).to(dev))
+    return e, policy.flat_parameters().to(dev)
+
+
+def meta_surrogate_loss(iter_replays, iter_policies, policy, baseline, params, anil):
+    """(mean surrogate loss, mean KL(new || old)) over the tasks at the current ``policy`` parameters."""
+    if anil:
+        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+    e, theta = _prepare(iter_replays, iter_policies, policy, baseline, params)
+    return e.loss_and_kl(theta)
+
+
+def meta_optimize_trpo(params, policy, baseline, iter_replays, iter_policies, anil=False):
+    """One TRPO meta-step: CG direction from the second-order meta-gradient and the Fisher-vector product of the KL,
+    step scaling by ``max_kl``, backtracking line search; updates ``policy`` in place like the reference."""
+    if anil:
+        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+    e, theta = _prepare(iter_replays, iter_policies, policy, baseline, params)
+    new, diag = e.meta_optimize(theta, params['max_kl'], params['ls_max_steps'], params['backtrack_factor'],
+                                params['outer_lr'])
+    policy.load_flat_parameters(new)
+    return diag

@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(ADV_THREADS) rl_adv_kernel(const XmRlAdvArgs a
     for (int k = end; k >= start; --k) { R = r[k] + tg * R; ret[k] = R; }
   }
   __syncthreads();
+  if (a.advantages)
+    for (int k = tid; k < n; k += ADV_THREADS) a.advantages[base + k] = (float)ret[k];
   // ---- ch.normalize: (x - mean) / (unbiased std + 1e-8) ----------------------------------------------------------------
   double part = 0.0;
   for (int k = tid; k < n; k += ADV_THREADS) part += ret[k];

@@ -123,6 +123,14 @@ class TrpoEngine:
         self._launch(a)
         return out
 
+    def a2c_loss(self, theta, stride=0, k=0):
+        """-mean(log_prob * normalised advantage) per task on replay k (``trpo_a2c_loss``, rl.py:346-358), values only."""
+        a = self._sweep_args(XM_RL_A2C, XM_RL_FORWARD, k)
+        a.theta, a.theta_task_stride = _p(theta), stride
+        a.task_loss = _p(self.task_loss)
+        self._launch(a)
+        return self.task_loss if k == 0 else self.task_loss * self.total_tasks
+
     def hvp(self, theta, v, v_stride, out):
         """out_t = v_t - lr * H_t(theta) v_t: the cotangent (or tangent -- H is symmetric) through the adaptation step."""
         a = self._sweep_args(XM_RL_A2C, XM_RL_HVP, 0)

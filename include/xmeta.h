@@ -318,6 +318,7 @@ typedef struct XmRlAdvArgs {
   const float* rewards; const float* dones;          /* [replays][n]            */
   float* coef;                                       /* [replays][n]            */
   float* returns;                                    /* optional [replays][n] discounted returns */
+  float* advantages;                                 /* optional [replays][n] un-normalised GAE advantages */
 } XmRlAdvArgs;
 int xm_rl_advantages(const XmRlAdvArgs* a, void* stream);
 

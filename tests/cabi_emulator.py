@@ -685,6 +685,8 @@ class EmulatedLib:
             nxt = torch.cat([boot[1:], torch.zeros(1, dtype=torch.float64)])
             td = r + a.gamma * (1 - d) * nxt - boot
             adv = scan(a.tau * a.gamma, td)
+            if a.advantages:
+                view(a.advantages + 4 * rp * n, (n,)).copy_(adv.float())
             if n > 1:
                 adv = (adv - adv.mean()) / (adv.std() + 1e-8)
             view(a.coef + 4 * rp * n, (n,)).copy_((a.coef_scale * adv).float())
@@ -761,9 +763,9 @@ class EmulatedLib:
                 base = view(a.base + 4 * t * a.base_task_stride, (P,)).double() if a.base else torch.zeros(P, dtype=torch.float64)
                 view(a.out + 4 * t * a.out_task_stride, (P,)).copy_((base + a.scale * res).float())
             if a.task_loss and l is not None:
-                view(a.task_loss + 4 * t, (1,))[0] = float(l)
+                view(a.task_loss + 4 * t, (1,))[0] = float(l.detach())
             if a.task_kl and kl is not None:
-                view(a.task_kl + 4 * t, (1,))[0] = float(kl)
+                view(a.task_kl + 4 * t, (1,))[0] = float(kl.detach())
         return 0
 
     def xm_bn_ema(self, rm, rv, stats, n_outer, outer_stride, n_inner, inner_stride, C, momentum, stream):

@@ -113,3 +113,38 @@ def test_meta_optimize_trpo_matches_reference_fixture(kdev):
     upd_ref = torch.from_numpy(g['theta1'] - g['theta0'])
     assert rel(new.cpu().double() - torch.from_numpy(g['theta0']), upd_ref) < 2e-3
     assert rel(new, torch.from_numpy(g['theta1'])) < 1e-4
+
+
+def test_reference_api_surface(kdev):
+    """The functions a user of core_functions/rl.py calls, with the reference's signatures: trpo_update on a deepcopy
+    of the policy per task (rl/maml_trpo.py:107-111), then meta_optimize_trpo mutating the policy in place."""
+    from copy import deepcopy
+    from exploring_meta_b200.core_functions import rl as xrl
+    from exploring_meta_b200.core_functions.policies import DiagNormalPolicy, LinearValue
+    g = np.load(GOLD)
+    torch.manual_seed(42)
+    policy = DiagNormalPolicy(2, 2, activation='tanh').to(kdev)
+    assert [k for k, _ in policy.named_parameters()] == ['sigma', 'mean.0.weight', 'mean.0.bias', 'mean.2.weight',
+                                                         'mean.2.bias', 'mean.4.weight', 'mean.4.bias']
+    policy.load_flat_parameters(torch.from_numpy(g['theta0']).float().to(kdev))      # the fixture's float64-initialised policy
+    baseline = LinearValue(2, CFG['value_reg'])
+    params = dict(CFG)
+    data = make_replays(int(g['tasks']), int(g['episodes']), int(g['horizon']), seed=int(g['seed']))
+    iter_replays, iter_policies = [], []
+    for sup, qry in data:
+        sup_r, qry_r = ch.Replay(**{k: sup[k] for k in ('states', 'actions', 'rewards', 'dones', 'next_states')}), qry
+        learner = xrl.trpo_update(sup_r, deepcopy(policy), baseline, CFG['inner_lr'], CFG['gamma'], CFG['tau'],
+                                  first_order=True)
+        iter_replays.append([sup_r, qry_r])
+        iter_policies.append(learner)
+    assert rel(torch.stack([p.flat_parameters() for p in iter_policies]), torch.from_numpy(g['old_params'])) < 1e-5
+    loss, kl = xrl.meta_surrogate_loss(iter_replays, iter_policies, policy, baseline, params, False)
+    assert abs(float(loss) - float(g['old_loss'])) < 1e-5 and abs(float(kl)) < 1e-9
+    adv = xrl.compute_advantages(baseline, CFG['tau'], CFG['gamma'], data[0][0]['rewards'].to(kdev),
+                                 data[0][0]['dones'].to(kdev), data[0][0]['states'].to(kdev),
+                                 data[0][0]['next_states'].to(kdev))
+    d64 = make_replays(int(g['tasks']), int(g['episodes']), int(g['horizon']), seed=int(g['seed']), dtype=torch.float64)
+    assert rel(adv, ro.compute_advantages(d64[0][0], CFG['tau'], CFG['gamma'], CFG['value_reg'])) < 2e-5
+    diag = xrl.meta_optimize_trpo(params, policy, baseline, iter_replays, iter_policies)
+    assert diag['ls_step'] == int(g['ls_step'])
+    assert rel(policy.flat_parameters(), torch.from_numpy(g['theta1'])) < 1e-4
