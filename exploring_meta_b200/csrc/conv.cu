@@ -257,7 +257,7 @@ int conv_img_try(const XmConvArgs* a, cudaStream_t stream);
 using namespace xm;
 
 extern "C" int xm_set_precision(int precise) {
-  g_precise = precise ? 1 : 0;
+  g_precise = precise < 0 ? 0 : (precise > 2 ? 2 : precise);
   return 0;
 }
 

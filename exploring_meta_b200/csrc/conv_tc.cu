@@ -25,6 +25,15 @@
 // therefore uses FOUR TMEM accumulators -- one per kernel row kh for the hi*hi terms (12 MMAs each) and one for
 // all small correction terms -- which the epilogue sums with round-to-nearest adds.
 //
+// FP16-split variant (template parameter F16, xm_set_precision(2)): the same 3-term expansion on kind::f16 -- twice the
+// tensor rate of kind::tf32 and half the shared-memory bytes per element, the two things that bound this kernel.
+// x * s = hi + lo * 2^-11 with hi = fp16(x * s), lo = fp16((x * s - hi) * 2^11): 22 significant bits, like the TF32 pair.
+// fp16 has 5 exponent bits, so every staged tile is scaled by a power of two s = 2^k chosen from the tile's own
+// absolute maximum (producer warps: register max -> shared atomicMax -> named barrier), the task's weight block by
+// its own; the drain multiplies by 2^-(ka + kb) (exact).  Elements 2^-28 below the tile maximum lose relative
+// precision -- invisible in sums that the large elements dominate.  Operand planes hold 8 channels (16 B of fp16), so
+// a shift by one position is still a 16-byte shift of the descriptor start address; K = 16 per MMA, 18 MMAs per tile.
+//
 // Pipeline (warp-specialised, 1 CTA per SM, 512 threads): warps 0-6 stage tiles (global -> TF32 split -> smem), one
 // elected lane of warp 7 issues the MMAs, warps 8-11 and 12-15 are two drain groups working on alternate tiles
 // (tcgen05.ld -> kw shift-add -> NHWC store + BatchNorm statistics; warp w reads TMEM lane quarter w%4).  Two
@@ -32,9 +41,12 @@
 // completion.  Measured (XM_TC_TIMING, scripts/gpu_tc_timing.sh): with two drain groups the producers' stores and the
 // MMAs' operand reads share the shared-memory bandwidth and bound a tile at ~2900 cycles (MMA stream alone ~2100).
 // 64-channel and stride-2 layers reuse this kernel through channel-block / full-resolution passes (conv_tc_try).
+#include <cuda_fp16.h>
 #include "tc.cuh"
 
 namespace xm {
+
+extern int g_precise;                 // conv.cu: 0 = 1xTF32, 1 = 3xTF32, 2 = 3xFP16-split on the tcgen05 conv kernel
 
 constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs
 constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11, 12-15)
@@ -45,6 +57,42 @@ constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
 constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows minus the two shifted-out rows
 constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
+// kind::f16: fp16 inputs (a_format = b_format = 0), fp32 accumulate
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
+
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// power-of-two scale 2^k that brings a maximum magnitude m into [2^14, 2^15) (fp16 overflows at 65520); k = 0 for m = 0
+__device__ __forceinline__ int f16_scale_exp(float m) {
+  if (!(m > 0.f)) return 0;
+  int k = 14 - (int)((__float_as_uint(m) >> 23) & 0xffu) + 127;
+  return max(-100, min(100, k));
+}
+__device__ __forceinline__ float exp2i(int k) { return __uint_as_float((uint32_t)(127 + k) << 23); }
+// 8 floats -> 8 fp16 hi + 8 fp16 scaled residuals, packed as two 16-byte vectors
+__device__ __forceinline__ void split_f16(const float4& a, const float4& b, float sc, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((x[2 * i] - back.x) * LO_SCALE, (x[2 * i + 1] - back.y) * LO_SCALE);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // 16-byte store, or (accumulate) a vector reduction into global memory: out += v, rounded like an fp32 add.
 __device__ __forceinline__ void put4(float* dst, const float4 v, int accumulate) {
@@ -71,11 +119,13 @@ struct ConvTcK {
   int src_cs, src_co, out_cs, out_co, w_cin, w_ao, w_bo;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NPLANES = 8;                      // channel-group planes of the A operand
-  constexpr int BFLOATS = 3 * 8 * 96 * 4;         // B[kh][c4][n = kw*32 + cout][4]
+  constexpr int NPLANES = F16 ? 4 : 8;            // channel-group planes of the A operand (16 B per row and plane)
+  constexpr int BFLOATS = F16 ? 3 * 4 * 96 * 4    // B[kh][c8][n = kw*32 + cout][8 halfs] (4-byte words)
+                              : 3 * 8 * 96 * 4;   // B[kh][c4][n = kw*32 + cout][4]
   const int plane = p.plane_bytes, set_bytes = NPLANES * plane;   // one hi (or lo) set
 
   float* Bhi = reinterpret_cast<float*>(smem);
@@ -84,6 +134,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   uint64_t* bars = reinterpret_cast<uint64_t*>(Abase + 4 * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* xch = reinterpret_cast<float*>(bars + 10);            // [tile & 3][half][4 warps][3][16] boundary rows
+  // FP16 variant: per-tile absolute maxima (float bits) and scale exponents, weight-block maximum / exponent
+  uint32_t* smax = reinterpret_cast<uint32_t*>(xch + 8 * 4 * 3 * 16);   // [4]
+  int* a_exp = reinterpret_cast<int*>(smax + 4);                         // [4]
+  uint32_t* wmax = reinterpret_cast<uint32_t*>(a_exp + 4);               // [1]
+  int* b_exp = reinterpret_cast<int*>(wmax + 1);                         // [1]
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
                  bar_tfree = smem_u32(bars + 6);
 
@@ -138,6 +193,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   // ---- resident weights, split into TF32 hi / lo: B[kh][k/4][n = kw*32 + out channel][k%4] ---------------
   {
     const float* W = p.w + (long long)task * p.wstride;       // [co][ci][3][3]
+    float wscale = 1.f;
+    if (F16) {                                                // power-of-two scale from the block's absolute maximum
+      if (tid == 0) { *wmax = 0u; smax[0] = smax[1] = smax[2] = smax[3] = 0u; }
+      __syncthreads();
+      float m = 0.f;
+      for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
+        const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);
+        m = fmaxf(m, fabsf(__ldg(W + ((long long)(p.w_ao + a) * p.w_cin + p.w_bo + b) * 9 + tap)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) atomicMax(wmax, __float_as_uint(m));
+      __syncthreads();
+      const int kb = f16_scale_exp(__uint_as_float(*wmax));
+      if (tid == 0) *b_exp = kb;
+      wscale = exp2i(kb);
+    }
     for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
       const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[w_ao + a][w_bo + b][tap]
       const float v = __ldg(W + ((long long)(p.w_ao + a) * p.w_cin + p.w_bo + b) * 9 + tap);
@@ -145,10 +217,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       if (p.wmode == 0) { n = a; k = b; t2 = tap; }           // forward: n = cout, k = cin
       else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
       const int kh = t2 / 3, kw = t2 - 3 * kh;
-      const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
-      const float hi = __uint_as_float(f2tf32(v));
-      Bhi[idx] = hi;
-      Blo[idx] = v - hi;
+      if (F16) {
+        const int idx = (((kh * 4 + (k >> 3)) * 96) + kw * 32 + n) * 8 + (k & 7);
+        const float x = v * wscale;
+        const __half h = __float2half_rn(x);
+        reinterpret_cast<__half*>(Bhi)[idx] = h;
+        reinterpret_cast<__half*>(Blo)[idx] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
+      } else {
+        const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
+        const float hi = __uint_as_float(f2tf32(v));
+        Bhi[idx] = hi;
+        Blo[idx] = v - hi;
+      }
     }
   }
   fence_proxy_async();
@@ -187,6 +267,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t_wait += clock64() - t0; t0 = clock64();
 #endif
+      if (F16) {
+        // tile scale: maximum magnitude over everything the producers stage for this tile
+        float m = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(&smax[it & 3], __float_as_uint(m));
+        asm volatile("bar.sync 3, %0;" ::"n"(TC_PRODUCERS) : "memory");
+        const int ka = f16_scale_exp(__uint_as_float(smax[it & 3]));
+        if (tid == 0) { a_exp[it & 3] = ka; smax[(it + 2) & 3] = 0u; }   // slot of tile it+2: its last readers passed this barrier
+        const float sc = exp2i(ka);
+        unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)c8 * plane;     // plane = channel octet
+        unsigned char* lo = hi + set_bytes;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jrow + PR * u;
+          if (j < p.R) {
+            uint4 h, l;
+            split_f16(v[2 * u], v[2 * u + 1], sc, h, l);
+            *reinterpret_cast<uint4*>(hi + (size_t)j * 16) = h;
+            *reinterpret_cast<uint4*>(lo + (size_t)j * 16) = l;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+        return;
+      }
       unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)(2 * c8) * plane;
       unsigned char* lo = hi + set_bytes;
 #pragma unroll
@@ -263,6 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       t_wait += clock64() - t0; t0 = clock64();
 #endif
       tc_fence_after();
+      const float unscale = F16 ? exp2i(-(a_exp[it & 3] + *b_exp)) : 1.f;
       const long long o_pair = __shfl_xor_sync(0xffffffffu, o, 1);
       const bool v_pair = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 192);
@@ -278,8 +388,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           tmem_ld16_nowait(taddr + 96 + kw * 32 + half * 16, r1);  // correction terms (small)
           tmem_ld16_nowait(taddr + kw * 32 + half * 16, r2);       // hi*hi terms
           tmem_ld_wait();
+          if (F16) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
+            for (int k = 0; k < 16; ++k) v[k] = fmaf(__uint_as_float(r1[k]), LO_UNSCALE, __uint_as_float(r2[k])) * unscale;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
+          }
           if (kw == 1) {
             // boundary rows for the previous warp: lane 0 publishes its kw = 1 block
             if (lane == 0) {
@@ -443,6 +558,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         const uint32_t a_hi0 = umma_desc_lo(a_base, (uint32_t)plane);
         const uint32_t a_lo0 = a_hi0 + (uint32_t)(set_bytes >> 4);
         const uint32_t kstep = (uint32_t)(2 * plane) >> 4;          // two channel-group planes per K = 8
+        if (F16) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t shift = (uint32_t)(kh * p.Wp);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {                          // K = 16 channels = two 8-channel planes
+              const uint32_t ao = shift + (uint32_t)ks * kstep;
+              const uint32_t bo = (uint32_t)((kh * 4 + 2 * ks) * 96);
+              umma_f16_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC_F16, (uint32_t)((kh | ks) != 0));
+              umma_f16_lh(d0 + 96, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC_F16, 1u);
+              umma_f16_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC_F16, (uint32_t)((kh | ks) != 0));
+            }
+          }
+        } else
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           const uint32_t shift = (uint32_t)(kh * p.Wp);             // 16 B units (one staged row = 16 B per plane)
@@ -486,11 +615,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   }
 }
 
-static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes) {
+static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes, bool f16) {
   R = 128 + 2 * Wp;
   const int rpad = R | 1;                 // odd row count per plane: conflict-free 16 B stores across planes
   plane_bytes = rpad * 16;
-  return (size_t)2 * (3 * 8 * 96 * 4) * 4 + (size_t)4 * 8 * plane_bytes + 10 * 8 + 8 * 4 * 3 * 16 * 4;
+  const int nplanes = f16 ? 4 : 8, bwords = f16 ? 3 * 4 * 96 * 4 : 3 * 8 * 96 * 4;
+  return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + 8 * 4 * 3 * 16 * 4 + 16 * 4;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
@@ -587,7 +717,9 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
   const bool multi = blocks > 1 || s2;
   if (!multi && a->src2 && a->stat_mode == XM_STAT_SUM_SQ) return 0;
   int R, plane_bytes;
-  const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes);
+  const bool f16 = g_precise == 2;
+  const size_t smem = conv_tc_smem(g.win + 1, R, plane_bytes, f16);
+  auto kern = f16 ? conv_tc_kernel<true> : conv_tc_kernel<false>;
   if (smem > 227 * 1024 || R > TC_PRODUCERS) return 0;      // each producer thread stages <= 4 rows per tile
   ConvTcK p{};
   p.tasks = g.tasks; p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
@@ -610,11 +742,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
     ctas = per_task * g.tasks;
   }
   dim3 grid(ctas);
-  static bool attr_set = false;
-  if (!attr_set) {
-    XM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  XM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * g.cout * sizeof(double), stream));
   const int npairs = a->src2 ? 2 : 1;
   if (!multi) {
@@ -624,7 +752,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
       p.wstride = pair ? a->w2_task_stride : a->w1_task_stride;
       p.accumulate = pair;                                   // second pair adds onto the first pass' output
       p.stat_mode = a->stat_mode;                            // {sum v, sum v*aux} are linear: each pass adds its share
-      conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+      kern<<<grid, TC_THREADS, smem, stream>>>(p);
       if (int rc = launched("xm_conv(tcgen05)")) return rc;
     }
     return 1;
@@ -652,7 +780,7 @@ int conv_tc_try(const XmConvArgs* a, cudaStream_t stream) {
         p.w_ao = 32 * (fwd ? ob : sb);                     // weight rows = output channels of the FORWARD conv
         p.w_bo = 32 * (fwd ? sb : ob);
         p.accumulate = (pair > 0 || sb > 0) ? 1 : 0;
-        conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+        kern<<<grid, TC_THREADS, smem, stream>>>(p);
         if (int rc = launched("xm_conv(tcgen05, channel block)")) return rc;
       }
   }

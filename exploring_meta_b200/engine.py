@@ -27,6 +27,8 @@ BN_EPS = 1e-5          # torch.nn.BatchNorm2d default, vision_models.py:168-174
 BN_MOMENTUM = 0.1
 # XM_NO_IMG_BLOCK=1 routes the first ConvBlock through the generic conv / bn / wgrad kernels (A/B comparison)
 _NO_IMG_BLOCK = os.environ.get('XM_NO_IMG_BLOCK', '') not in ('', '0')
+# XM_SIDE_STREAM=0 keeps every call on one stream (A/B comparison of the parallel weight-gradient branch)
+_SIDE_STREAM = os.environ.get('XM_SIDE_STREAM', '1') not in ('', '0')
 
 
 def _require_cuda(device):
@@ -42,29 +44,68 @@ def _p(t, off=0):
 
 
 class _Program:
-    """A recorded list of C-ABI calls: (function, argument block)."""
+    """A recorded list of C-ABI calls: (function, argument block, name, lane).
+
+    Lane 1 calls may run concurrently with the main lane between a ``fork()`` and the next ``join()``: the weight
+    gradients of a block are off the critical path of the backward chain (bn_bwd -> dgrad -> bn_bwd -> ...), so at
+    small task counts, where a kernel does not fill the GPU, they overlap with it on a second stream (captured into
+    the same CUDA graph as a parallel branch).  ``replay(stream)`` without ``side`` runs everything in order on one
+    stream."""
+    FORK, JOIN = 'fork', 'join'
 
     def __init__(self, lib, conv_ws=None):
         self.lib = lib
         self.calls = []
+        self.ops = []                    # calls interleaved with fork / join markers
         self.conv_ws = conv_ws          # workspace handed to every xm_conv call (stride-2 layers on the tcgen05 path)
+        self._forked = False
 
-    def emit(self, name, args):
+    def emit(self, name, args, lane=0):
         if name == 'xm_conv' and self.conv_ws is not None:
             args.workspace, args.workspace_bytes = _p(self.conv_ws), self.conv_ws.numel() * 4
-        self.calls.append((getattr(self.lib, name), args, name))
+        call = (getattr(self.lib, name), args, name)
+        self.calls.append(call)
+        if lane == 1:
+            self.ops.append((self.FORK,))       # side lane waits for everything issued on the main lane so far
+            self._forked = True
+        self.ops.append(call + (lane,))
 
     def emit_raw(self, name, *argv):
-        self.calls.append((getattr(self.lib, name), argv, name))
+        call = (getattr(self.lib, name), argv, name)
+        self.calls.append(call)
+        self.ops.append(call + (0,))
 
-    def replay(self, stream):
-        for fn, args, name in self.calls:
-            if isinstance(args, tuple):
-                code = fn(*args, stream)
+    def join(self):
+        """Main lane waits for the side lane (no-op if nothing was forked since the last join)."""
+        if self._forked:
+            self.ops.append((self.JOIN,))
+            self._forked = False
+
+    @staticmethod
+    def _call(fn, args, name, stream):
+        code = fn(*args, stream) if isinstance(args, tuple) else fn(ctypes.byref(args), stream)
+        if code != 0:
+            _lib.check(code, name)
+
+    def replay(self, stream, main=None, side=None):
+        """``stream``: raw handle of the main stream.  With ``main`` / ``side`` (torch.cuda.Stream objects, ``main``
+        wrapping ``stream``) lane-1 calls go to ``side`` with event dependencies."""
+        if side is None:
+            for fn, args, name in self.calls:
+                self._call(fn, args, name, stream)
+            return
+        for op in self.ops:
+            if op[0] == self.FORK:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+            elif op[0] == self.JOIN:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
             else:
-                code = fn(ctypes.byref(args), stream)
-            if code != 0:
-                _lib.check(code, name)
+                fn, args, name, lane = op
+                self._call(fn, args, name, side.cuda_stream if lane == 1 else stream)
 
 
 class _EngineBase:
@@ -226,18 +267,28 @@ class _EngineBase:
         w.base_w, w.base_b, w.base_task_stride = _p(base, o[4 * l + 2]), _p(base, o[4 * l + 3]), base_stride
         w.scale = scale
         w.partial, w.partial_bytes = _p(self.wg_partial), self.wg_partial.numel() * 4
-        prog.emit('xm_wgrad', w)
+        prog.emit('xm_wgrad', w, lane=1)      # off the critical path: parallel branch (one scratch buffer: all on lane 1)
 
     # ---- execution ----------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
+
+    def replay(self, parallel=True):
+        """Issues the program on the current stream; with ``parallel`` the side-lane calls (weight gradients) go to a
+        second stream that forks from / joins into it (inside a capture this becomes a parallel graph branch)."""
+        if not (parallel and _SIDE_STREAM and self.device.type == 'cuda'):
+            return self.prog.replay(self._stream())
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        self.prog.replay(main.cuda_stream, main, self._side)
 
     def launch(self):
         """Replays the program on the current stream (asynchronous)."""
         if self._graph is not None:
             self._graph.replay()
         else:
-            self.prog.replay(self._stream())
+            self.replay()
 
     def capture(self):
         """Captures the launch program into a CUDA graph; subsequent ``launch()`` calls replay it."""
@@ -251,7 +302,7 @@ class _EngineBase:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.prog.replay(torch.cuda.current_stream(self.device).cuda_stream)
+            self.replay()
         self._graph = graph
 
     @property
@@ -318,9 +369,10 @@ class MamlEngine(_EngineBase):
         self.tMI = [self._f32(B, 2, C) for l in range(L)]
         self.tBR = [self._f32(B, 2, C) for l in range(L)]
         self.tDR = [self._f32(B, 2, C) for l in range(L)]
-        zmax = max([self.tZ[l].numel() for l in range(l0, L)] or [1])
-        self.GZ = self._f32(zmax)
-        self.GZdot = self._f32(zmax) if mode == 'second' else None
+        # pre-BN cotangents, one buffer per layer: the weight gradient of layer l (parallel branch) reads GZ[l] while the
+        # main chain is already producing GZ[l-1]
+        self.GZ = [None if l < l0 else self._f32(self.tZ[l].numel()) for l in range(L)]
+        self.GZdot = [None if (l < l0 or mode != 'second') else self._f32(self.tZ[l].numel()) for l in range(L)]
         self.bar = [self._f32(B, P), self._f32(B, P)] if mode != 'eval' else None
         self.prog = _Program(self.lib, self.conv_ws)
         self._build()
@@ -369,6 +421,7 @@ class MamlEngine(_EngineBase):
             k = t if self.mode == 'second' else 0
             th, ts = self._theta(t)
             nxt = self.theta_steps[t]
+            prog.join()                                # theta_t complete (weight gradients of step t-1 run on the side lane)
             for l in range(L):
                 self._emit_block_fwd(prog, l, S, self.Pa[k][l - 1] if l else None, sup, th, ts,
                                      self.Z[k][l], self.Pa[k][l], self.MI[k][l], self.call_stats[t, l])
@@ -376,10 +429,11 @@ class MamlEngine(_EngineBase):
                             nxt, P, th, ts, -self.lr)
             for l in reversed(range(L)):
                 self._emit_block_bwd(prog, l, S, self.Pa[k][l - 1] if l else None, sup, th, ts,
-                                     self.Z[k][l], self.GP[k][l], self.MI[k][l], self.BR[k][l], self.GZ,
+                                     self.Z[k][l], self.GP[k][l], self.MI[k][l], self.BR[k][l], self.GZ[l],
                                      self.GP[k][l - 1] if l else None, nxt, P, th, ts, -self.lr)
         # ---- phase 2: query loss / accuracy at theta_T (vision.py:15-17) and its gradient -----
         th, ts = self._theta(T)
+        prog.join()
         for l in range(L):
             self._emit_block_fwd(prog, l, S, self.tP[l - 1] if l else None, qry, th, ts,
                                  self.tZ[l], self.tP[l], self.tMI[l], self.call_stats[T, l])
@@ -392,7 +446,7 @@ class MamlEngine(_EngineBase):
                         loss=self.loss, correct=self.correct)
         for l in reversed(range(L)):
             self._emit_block_bwd(prog, l, S, self.tP[l - 1] if l else None, qry, th, ts,
-                                 self.tZ[l], self.tGP[l], self.tMI[l], self.tBR[l], self.GZ,
+                                 self.tZ[l], self.tGP[l], self.tMI[l], self.tBR[l], self.GZ[l],
                                  self.tGP[l - 1] if l else None, bar, P, None, 0, 1.0)
         # ---- phase 3: bar_t = bar_{t+1} - lr * H(theta_t) bar_{t+1}, t = T-1 .. 0 (second order) ----
         cur = 0
@@ -401,6 +455,7 @@ class MamlEngine(_EngineBase):
                 self._emit_dual_step(prog, t, self.bar[cur], self.bar[1 - cur])
                 cur = 1 - cur
         # ---- sum over tasks in task order = accumulation into the master .grad (maml_vision.py:112) --
+        prog.join()
         prog.emit_raw('xm_accumulate_tasks', _p(self.bar[cur]), P, self.tasks, P, _p(self.grad), 0)
 
     def _emit_dual_step(self, prog, t, v, out):
@@ -410,6 +465,7 @@ class MamlEngine(_EngineBase):
         sup = (0, 2, self.rows)
         th, ts = self._theta(t)
         Z, Pa, GP, MI, BR = self.Z[t], self.Pa[t], self.GP[t], self.MI[t], self.BR[t]
+        prog.join()                                    # v complete; the previous sweep's readers of tP / GZ are done
         for l in range(L):
             if l == 0 and self.img:          # fused image block: zdot only at the winners, statistics from the Gram matrix
                 gram, st = Z[0]
@@ -463,7 +519,7 @@ class MamlEngine(_EngineBase):
             b.gamma, b.beta, b.gb_task_stride = _p(th, o[4 * l]), _p(th, o[4 * l + 1]), ts
             b.gamma_dot, b.beta_dot, b.gbdot_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
             # gz is re-derived only where a consumer needs it: dgrad / wgrad pair 2 of layers with a tangent input
-            b.gz, b.gzdot = (_p(self.GZ) if l > 0 else None), _p(self.GZdot)
+            b.gz, b.gzdot = (_p(self.GZ[l]) if l > 0 else None), _p(self.GZdot[l])
             b.out_gamma, b.out_beta, b.out_task_stride = _p(out, o[4 * l]), _p(out, o[4 * l + 1]), P
             b.base_gamma, b.base_beta, b.base_task_stride = _p(v, o[4 * l]), _p(v, o[4 * l + 1]), P
             b.scale = -self.lr
@@ -472,8 +528,8 @@ class MamlEngine(_EngineBase):
             if l > 0:                        # gxdot = dgrad(gzdot, W) + dgrad(gz, Wdot)
                 d = XmConvArgs()
                 d.g, d.mode, d.stat_mode = self.geom(l, S), XM_CONV_DGRAD, XM_STAT_NONE
-                d.src1, d.w1, d.w1_task_stride = _p(self.GZdot), _p(th, o[4 * l + 2]), ts
-                d.src2, d.w2, d.w2_task_stride = _p(self.GZ), _p(v, o[4 * l + 2]), P
+                d.src1, d.w1, d.w1_task_stride = _p(self.GZdot[l]), _p(th, o[4 * l + 2]), ts
+                d.src2, d.w2, d.w2_task_stride = _p(self.GZ[l]), _p(v, o[4 * l + 2]), P
                 d.out = _p(self.tGP[l - 1])
                 prog.emit('xm_conv', d)
             w = XmWgradArgs()                # gWdot = wgrad(x, gzdot) + wgrad(xdot, gz)
@@ -483,13 +539,13 @@ class MamlEngine(_EngineBase):
                 w.x1 = _p(self.x)
             else:
                 w.x1 = _p(Pa[l - 1])
-                w.x2, w.g2 = _p(self.tP[l - 1]), _p(self.GZ)
-            w.g1 = _p(self.GZdot)
+                w.x2, w.g2 = _p(self.tP[l - 1]), _p(self.GZ[l])
+            w.g1 = _p(self.GZdot[l])
             w.out_w, w.out_b, w.out_task_stride = _p(out, o[4 * l + 2]), _p(out, o[4 * l + 3]), P
             w.base_w, w.base_b, w.base_task_stride = _p(v, o[4 * l + 2]), _p(v, o[4 * l + 3]), P
             w.scale = -self.lr
             w.partial, w.partial_bytes = _p(self.wg_partial), self.wg_partial.numel() * 4
-            prog.emit('xm_wgrad', w)
+            prog.emit('xm_wgrad', w, lane=1)
 
     # ---- convenience ----------------------------------------------------------------------------
     def run(self, x=None, y=None, theta=None):
@@ -552,7 +608,7 @@ class AnilEngine(_EngineBase):
         self.GP = [self._f32(*self.pshape(l, R)) for l in range(L)]
         self.MI = [self._f32(B, 2, C) for l in range(L)]
         self.BR = [self._f32(B, 2, C) for l in range(L)]
-        self.GZ = self._f32(max([self.Z[l].numel() for l in range(l0, L)] or [1]))
+        self.GZ = [None if l < l0 else self._f32(self.Z[l].numel()) for l in range(L)]
         self.task_grad = self._f32(B, P)
         self.task_head_grad = self._f32(B, self.PH)
         self.prog = _Program(self.lib, self.conv_ws)
@@ -583,8 +639,9 @@ class AnilEngine(_EngineBase):
             return
         for l in reversed(range(L)):
             self._emit_block_bwd(prog, l, R, self.Pa[l - 1] if l else None, rows, self.theta, 0,
-                                 self.Z[l], self.GP[l], self.MI[l], self.BR[l], self.GZ,
+                                 self.Z[l], self.GP[l], self.MI[l], self.BR[l], self.GZ[l],
                                  self.GP[l - 1] if l else None, self.task_grad, P, None, 0, 1.0)
+        prog.join()
         prog.emit_raw('xm_accumulate_tasks', _p(self.task_grad), P, B, P, _p(self.grad), 0)
         prog.emit_raw('xm_accumulate_tasks', _p(self.task_head_grad), self.PH, B, self.PH, _p(self.head_grad), 0)
 

@@ -200,7 +200,7 @@ class MamlTrainer(_TrainerBase):
 
     def _step_body(self, track_running_stats=True):
         e = self.engine
-        e.prog.replay(self._stream())
+        e.replay()
         if track_running_stats and self.world == 1:
             e.update_running_stats(self.running_mean, self.running_var)
         elif track_running_stats:
@@ -274,7 +274,7 @@ class AnilTrainer(_TrainerBase):
         return e.loss, e.correct
 
     def _step_body(self):
-        self.engine.prog.replay(self._stream())
+        self.engine.replay()
         self._reduce_and_step(self.theta_all, self.tasks * self.world)
 
     def metrics(self):

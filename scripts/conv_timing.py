@@ -6,6 +6,7 @@ from exploring_meta_b200 import _lib
 from exploring_meta_b200._lib import XmBlockGeom, XmConvArgs
 lib = _lib.load()
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 42
+lib.xm_set_precision(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 g = XmBlockGeom(32, 25, 32, 32, H, H, H, H, H // 2, H // 2, 1, 1)
 x = torch.randn(32, 25, H, H, 32, device='cuda'); w = torch.randn(32, 32 * 32 * 9, device='cuda') * 0.05
 out = torch.empty_like(x); stats = torch.zeros(32, 2, 32, dtype=torch.float64, device='cuda')
