@@ -67,6 +67,7 @@ def parse():
     ap.add_argument('--tasks', type=int, default=0, help='tasks per GPU (default: from --config and --scaling)')
     ap.add_argument('--inner-steps', type=int, default=0, help='override the config\'s inner steps')
     ap.add_argument('--fast-tf32', action='store_true', help='single-pass TF32 contractions (not parity-grade)')
+    ap.add_argument('--precision', type=int, default=-1, help='xm_set_precision value (default: library default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-breakdown', action='store_true')
     ap.add_argument('--no-weak', action='store_true', help='skip the extra weak-scaling leg of a strong N>1 run')
@@ -334,7 +335,10 @@ def run_ours(args):
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     lib = _lib.load()
-    lib.xm_set_precision(0 if args.fast_tf32 else 1)
+    if args.fast_tf32:
+        lib.xm_set_precision(0)
+    elif args.precision >= 0:
+        lib.xm_set_precision(args.precision)
 
     cfg = CONFIGS[args.config]
     T = args.inner_steps or cfg['steps']

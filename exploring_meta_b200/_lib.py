@@ -202,6 +202,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
+    if os.environ.get('XM_PRECISION'):            # A/B switch of the contraction precision (see xm_set_precision)
+        lib.xm_set_precision(int(os.environ['XM_PRECISION']))
     _lib = lib
     return lib
 

@@ -32,7 +32,11 @@
 // absolute maximum (producer warps: register max -> shared atomicMax -> named barrier), the task's weight block by
 // its own; the drain multiplies by 2^-(ka + kb) (exact).  Elements 2^-28 below the tile maximum lose relative
 // precision -- invisible in sums that the large elements dominate.  Operand planes hold 8 channels (16 B of fp16), so
-// a shift by one position is still a 16-byte shift of the descriptor start address; K = 16 per MMA, 18 MMAs per tile.
+// a shift by one position is still a 16-byte shift of the descriptor start address.  The taps are NOT stacked in N here:
+// nine taps x two K = 16 steps x three terms = 54 MMAs (M = 128, N = 32) accumulate into the same 32 columns, so
+// accumulator row i is output position q0 + i and the drain -- which bounds the TF32 kernel (XM_TC_TIMING: ~7000 cycles of
+// TMEM loads, kw shift-add shuffles, boundary exchange, stores and statistics per tile and drain group against ~2300
+// cycles of MMAs) -- loses its cross-lane shift-add, the group barrier and the boundary fix-up.
 //
 // Pipeline (warp-specialised, 1 CTA per SM, 512 threads): warps 0-6 stage tiles (global -> TF32 split -> smem), one
 // elected lane of warp 7 issues the MMAs, warps 8-11 and 12-15 are two drain groups working on alternate tiles
@@ -44,13 +48,17 @@
 #include <cuda_fp16.h>
 #include "tc.cuh"
 
+#ifndef XM_TC_GROUPS
+#define XM_TC_GROUPS 2
+#endif
+
 namespace xm {
 
 extern int g_precise;                 // conv.cu: 0 = 1xTF32, 1 = 3xTF32, 2 = 3xFP16-split on the tcgen05 conv kernel
 
 constexpr int TC_PRODUCERS = 224;     // warps 0-6; warp 7 issues the MMAs
 constexpr int TC_DRAINERS = 128;      // per drain group (warps 8-11, 12-15)
-constexpr int TC_GROUPS = 2;          // drain groups: group g drains tiles g, g + 2, ... (= TMEM set g): a tile's drain is
+constexpr int TC_GROUPS = XM_TC_GROUPS;          // drain groups: group g drains tiles g, g + G, ...: a tile's drain is
                                       // latency-bound (TMEM loads, shuffles, exchange) and ~1.5x the MMA time of a tile,
                                       // so two tiles are drained concurrently (16 warps: 128 registers each)
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
@@ -58,7 +66,7 @@ constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows 
 constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
 // kind::f16: fp16 inputs (a_format = b_format = 0), fp32 accumulate
-constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // M = 128, N = 32 (one tap)
 constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
 
 __device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
@@ -133,22 +141,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   unsigned char* Abase = smem + 2 * BFLOATS * 4;               // stage s: hi at s*2*set, lo at (s*2+1)*set
   uint64_t* bars = reinterpret_cast<uint64_t*>(Abase + 4 * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* xch = reinterpret_cast<float*>(bars + 10);            // [tile & 3][half][4 warps][3][16] boundary rows
+  float* xch = reinterpret_cast<float*>(bars + 10);            // [group][tile parity][half][4 warps][3][16] boundary rows
   // FP16 variant: per-tile absolute maxima (float bits) and scale exponents, weight-block maximum / exponent
-  uint32_t* smax = reinterpret_cast<uint32_t*>(xch + 8 * 4 * 3 * 16);   // [4]
+  uint32_t* smax = reinterpret_cast<uint32_t*>(xch + TC_GROUPS * 2 * 2 * 4 * 3 * 16);   // [4]
   int* a_exp = reinterpret_cast<int*>(smax + 4);                         // [4]
   uint32_t* wmax = reinterpret_cast<uint32_t*>(a_exp + 4);               // [1]
   int* b_exp = reinterpret_cast<int*>(wmax + 1);                         // [1]
-  const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
-                 bar_tfree = smem_u32(bars + 6);
+  uint64_t* mxbars = reinterpret_cast<uint64_t*>(smax + 12);             // [2] "every producer warp has posted its tile maximum"
+  const uint32_t bar_max = smem_u32(mxbars);
+  // "accumulators of a tile complete": ONE BARRIER PER DRAIN GROUP (tile it -> barrier it % G, phase it / G).  A group
+  // sees every phase of its own barrier, and the barrier can run at most one phase ahead of the group (the MMAs of tile
+  // it + G need the TMEM set that tile it + G - 2 releases, which needs tile it's set released first), so the parity
+  // wait is unambiguous -- per-set barriers are not: a group would see only every G-th phase of them.
+  const uint32_t bar_tfull = smem_u32(mxbars + 2);
+  const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfree = smem_u32(bars + 6);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full + 8 * s, TC_PRODUCERS);
       mbar_init(bar_sfree + 8 * s, 1);
-      mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tfree + 8 * s, TC_DRAINERS);
+      if (F16) mbar_init(bar_max + 8 * s, TC_PRODUCERS / 32);
     }
+    for (int g = 0; g < TC_GROUPS; ++g) mbar_init(bar_tfull + 8 * g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 7) {
@@ -184,9 +199,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_full + 8 * s, TC_PRODUCERS);
         mbar_init(bar_sfree + 8 * s, 1);
-        mbar_init(bar_tfull + 8 * s, 1);
         mbar_init(bar_tfree + 8 * s, TC_DRAINERS);
+        if (F16) mbar_init(bar_max + 8 * s, TC_PRODUCERS / 32);
       }
+      for (int g = 0; g < TC_GROUPS; ++g) mbar_init(bar_tfull + 8 * g, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
       const int kh = t2 / 3, kw = t2 - 3 * kh;
       if (F16) {
-        const int idx = (((kh * 4 + (k >> 3)) * 96) + kw * 32 + n) * 8 + (k & 7);
+        const int idx = ((((kh * 3 + kw) * 4 + (k >> 3)) * 32) + n) * 8 + (k & 7);   // B[tap][c8][n][8 halfs]
         const float x = v * wscale;
         const __half h = __float2half_rn(x);
         reinterpret_cast<__half*>(Bhi)[idx] = h;
@@ -263,22 +279,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t0 = clock64();
 #endif
-      if (it >= 2) mbar_wait(bar_sfree + 8 * s, ((it - 2) >> 1) & 1);   // MMAs of tile it-2 have read stage s
-#ifdef XM_TC_TIMING
-      t_wait += clock64() - t0; t0 = clock64();
-#endif
       if (F16) {
-        // tile scale: maximum magnitude over everything the producers stage for this tile
+        // tile scale: maximum magnitude over everything the producers stage for this tile.  Each warp posts its maximum
+        // and arrives on an mbarrier BEFORE waiting for the stage, so the handshake hides behind that wait.
         float m = 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(&smax[it & 3], __float_as_uint(m));
-        asm volatile("bar.sync 3, %0;" ::"n"(TC_PRODUCERS) : "memory");
+        if (lane == 0) {
+          atomicMax(&smax[it & 3], __float_as_uint(m));
+          mbar_arrive(bar_max + 8 * s);
+        }
+      }
+      if (it >= 2) mbar_wait(bar_sfree + 8 * s, ((it - 2) >> 1) & 1);   // MMAs of tile it-2 have read stage s
+#ifdef XM_TC_TIMING
+      t_wait += clock64() - t0; t0 = clock64();
+#endif
+      if (F16) {
+        mbar_wait(bar_max + 8 * s, (it >> 1) & 1);
         const int ka = f16_scale_exp(__uint_as_float(smax[it & 3]));
-        if (tid == 0) { a_exp[it & 3] = ka; smax[(it + 2) & 3] = 0u; }   // slot of tile it+2: its last readers passed this barrier
+        // slot (it + 2) & 3 was last read for tile it - 2: every producer has since passed two of these waits
+        if (tid == 0) { a_exp[it & 3] = ka; smax[(it + 2) & 3] = 0u; }
         const float sc = exp2i(ka);
         unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)c8 * plane;     // plane = channel octet
         unsigned char* lo = hi + set_bytes;
@@ -294,6 +317,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
+#ifdef XM_TC_TIMING
+        t_load += clock64() - t0;
+#endif
         return;
       }
       unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)(2 * c8) * plane;
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     // lets 16 warps fit the register file)
     double dsum = 0.0, dsq = 0.0;
 #ifdef XM_TC_TIMING
-    long long t_wait = 0, t_tmem = 0, t_rest = 0, t0;
+    long long t_wait = 0, t_tmem = 0, t_rest = 0, t0, t_bar = 0, t_fix = 0, t_store = 0, t_stat = 0;
 #endif
     for (int it = group; it < ntiles; it += TC_GROUPS) {
       const int s = it & 1;
@@ -367,19 +393,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       // tangent statistics multiply by one 128 B aux row per accumulator row: pull it into L1 while the warp waits
       // for the accumulators, so the loads in the epilogue do not expose HBM latency inside the drain
       if (p.stat_mode == XM_STAT_SUM_AUX && valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.aux + o));
-      mbar_wait(bar_tfull + 8 * s, (it >> 1) & 1);
+      mbar_wait(bar_tfull + 8 * group, (it / TC_GROUPS) & 1);
 #ifdef XM_TC_TIMING
       t_wait += clock64() - t0; t0 = clock64();
 #endif
       tc_fence_after();
+      const int xslot = group * 2 + ((it / TC_GROUPS) & 1);       // boundary-row exchange: two alternating slots per group
       const float unscale = F16 ? exp2i(-(a_exp[it & 3] + *b_exp)) : 1.f;
       const long long o_pair = __shfl_xor_sync(0xffffffffu, o, 1);
       const bool v_pair = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 192);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * (F16 ? 64 : 192));
       // ---- TMEM phase: both 16-column halves -> registers (kw shifts applied), then the set is released --------
       auto load_half = [&](int half, float (&acc)[16]) {
         // one 16-column block at a time (register pressure): kw = 1, kw = 2, then the thread's own kw = 0 block
-        float* xb = xch + ((((it & 3) * 2 + half) * 4 + quarter) * 3) * 16;
+        float* xb = xch + (((xslot * 2 + half) * 4 + quarter) * 3) * 16;
 #pragma unroll
         for (int blk = 1; blk <= 3; ++blk) {
           const int kw = blk % 3;                                  // 1, 2, 0
@@ -388,13 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           tmem_ld16_nowait(taddr + 96 + kw * 32 + half * 16, r1);  // correction terms (small)
           tmem_ld16_nowait(taddr + kw * 32 + half * 16, r2);       // hi*hi terms
           tmem_ld_wait();
-          if (F16) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = fmaf(__uint_as_float(r1[k]), LO_UNSCALE, __uint_as_float(r2[k])) * unscale;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
-          }
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
           if (kw == 1) {
             // boundary rows for the previous warp: lane 0 publishes its kw = 1 block
             if (lane == 0) {
@@ -423,21 +445,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         }
       };
       float acc2[2][16];
-      load_half(0, acc2[0]);
-      load_half(1, acc2[1]);
+      if (F16) {
+        // unstacked taps: accumulator row i IS output position q0 + i -- columns [0, 32) hi*hi, [32, 64) corrections
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r1[16], r2[16];
+          tmem_ld16_nowait(taddr + 32 + half * 16, r1);
+          tmem_ld16_nowait(taddr + half * 16, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            acc2[half][k] = fmaf(__uint_as_float(r1[k]), LO_UNSCALE, __uint_as_float(r2[k])) * unscale;
+        }
+      } else {
+        load_half(0, acc2[0]);
+        load_half(1, acc2[1]);
+      }
       tc_fence_before();
       mbar_arrive(bar_tfree + 8 * s);                            // TMEM set s may be overwritten
 #ifdef XM_TC_TIMING
       t_tmem += clock64() - t0; t0 = clock64();
 #endif
-      if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the group's four warps: boundary rows published
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (lane >= 30) {
+      if (!F16) asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");   // the group's four warps: boundary rows published
+#ifdef XM_TC_TIMING
+      t_bar += clock64() - t0; t0 = clock64();
+#endif
+      if (!F16 && lane >= 30) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
           // (16-byte loads, all issued before the first use: one shared-memory round trip instead of 48)
-          const float4* xn = reinterpret_cast<const float4*>(xch + ((((it & 3) * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
+          const float4* xn = reinterpret_cast<const float4*>(xch + (((xslot * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
           float4 a[4], b[4];
           const int oa = lane == 31 ? 0 : 4;                     // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
 #pragma unroll
@@ -450,6 +488,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           }
         }
       }
+#ifdef XM_TC_TIMING
+      __syncwarp();
+      t_fix += clock64() - t0; t0 = clock64();
+#endif
       // ---- epilogue of both halves: (accumulate), statistics, paired full-sector stores --------------------------
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -483,6 +525,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           }
         }
       }
+#ifdef XM_TC_TIMING
+      t_store += clock64() - t0; t0 = clock64();
+#endif
       if (p.stat_mode) {
         // v1 = this row's 32 outputs (0 for rows that produce none), v2 = v1^2 or v1 * aux
         float v1[32], v2[32];
@@ -516,12 +561,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         dsum += (double)v1[0];
         dsq += (double)v2[0];
       }
+#ifdef XM_TC_TIMING
+      t_stat += clock64() - t0;
+#endif
     }
 #ifdef XM_TC_TIMING
     t_rest = clock64() - t0;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == TC_PRODUCERS + 32)
-      printf("drainer: wait %lld tmem-phase %lld (per tile %lld / %lld) last-rest %lld\n", t_wait, t_tmem,
-             t_wait / ntiles, t_tmem / ntiles, t_rest);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == TC_PRODUCERS + 32 || tid == TC_PRODUCERS + 32 + 127)) {
+      const int nd = (ntiles - group + TC_GROUPS - 1) / TC_GROUPS;
+      printf("drainer tid %d: per DRAINED tile: wait %lld tmem %lld group-barrier %lld fix-up %lld stores %lld stats %lld\n", tid,
+             t_wait / nd, t_tmem / nd, t_bar / nd, t_fix / nd, t_store / nd, t_stat / nd);
+    }
 #endif
     if (p.stat_mode) {
       // lane l holds channel l's sums over this warp's rows of all its tiles
@@ -534,6 +584,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     // the [8 x 96] weight slab of the three kw taps; 3 expansion terms -> 36 MMAs (M=128, N=96, K=8).
 #ifdef XM_TC_TIMING
     long long t_wf = 0, t_wt = 0, t_issue = 0, t0;
+    unsigned long long ns0, ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    const long long c_begin = clock64();
 #endif
     for (int it = 0; it < ntiles; ++it) {
       const int s = it & 1;
@@ -559,16 +612,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         const uint32_t a_lo0 = a_hi0 + (uint32_t)(set_bytes >> 4);
         const uint32_t kstep = (uint32_t)(2 * plane) >> 4;          // two channel-group planes per K = 8
         if (F16) {
+          // one MMA per (tap, 16-channel K step, expansion term): M = 128, N = 32, K = 16.  The tap's A operand is the
+          // staged halo at row offset kh*Wp + kw, so all nine taps accumulate into the SAME 32 columns: accumulator row i
+          // is output position q0 + i, and the drain needs no cross-lane kw shift-add (54 MMAs, 2 x 32 TMEM columns).
+          const uint32_t bf_hi0 = umma_desc_lo(smem_u32(Bhi), 32u * 16u), bf_lo0 = umma_desc_lo(smem_u32(Blo), 32u * 16u);
+          const uint32_t df = tmem_base + (uint32_t)(s * 64);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t shift = (uint32_t)(kh * p.Wp);
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3));
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {                          // K = 16 channels = two 8-channel planes
               const uint32_t ao = shift + (uint32_t)ks * kstep;
-              const uint32_t bo = (uint32_t)((kh * 4 + 2 * ks) * 96);
-              umma_f16_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC_F16, (uint32_t)((kh | ks) != 0));
-              umma_f16_lh(d0 + 96, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC_F16, 1u);
-              umma_f16_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC_F16, (uint32_t)((kh | ks) != 0));
+              const uint32_t bo = (uint32_t)((tap * 4 + 2 * ks) * 32);
+              const uint32_t acc = (uint32_t)((tap | ks) != 0);
+              umma_f16_lh(df + 32, a_lo0 + ao, dhi, bf_hi0 + bo, dhi, TC_IDESC_F16, acc);
+              umma_f16_lh(df + 32, a_hi0 + ao, dhi, bf_lo0 + bo, dhi, TC_IDESC_F16, 1u);
+              umma_f16_lh(df, a_hi0 + ao, dhi, bf_hi0 + bo, dhi, TC_IDESC_F16, acc);
             }
           }
         } else
@@ -591,7 +650,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           }
         }
         umma_commit(bar_sfree + 8 * s);     // shared-memory stage s consumed
-        umma_commit(bar_tfull + 8 * s);     // accumulators of this tile complete
+        umma_commit(bar_tfull + 8 * (it % TC_GROUPS));     // accumulators of this tile complete: its drain group's barrier
       }
       __syncwarp();
 #ifdef XM_TC_TIMING
@@ -599,9 +658,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #endif
     }
 #ifdef XM_TC_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
     if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-      printf("mma: wait-full %lld wait-tfree %lld issue %lld (per tile %lld / %lld / %lld)\n", t_wf, t_wt, t_issue,
-             t_wf / ntiles, t_wt / ntiles, t_issue / ntiles);
+      printf("mma: wait-full %lld wait-tfree %lld issue %lld (per tile %lld / %lld / %lld); %lld cycles in %llu ns = %.3f GHz\n",
+             t_wf, t_wt, t_issue, t_wf / ntiles, t_wt / ntiles, t_issue / ntiles, clock64() - c_begin, ns1 - ns0,
+             (double)(clock64() - c_begin) / (double)(ns1 - ns0));
 #endif
   }
 
@@ -620,7 +681,7 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes, bool f16) {
   const int rpad = R | 1;                 // odd row count per plane: conflict-free 16 B stores across planes
   plane_bytes = rpad * 16;
   const int nplanes = f16 ? 4 : 8, bwords = f16 ? 3 * 4 * 96 * 4 : 3 * 8 * 96 * 4;
-  return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + 8 * 4 * 3 * 16 * 4 + 16 * 4;
+  return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + (size_t)TC_GROUPS * 2 * 2 * 4 * 3 * 16 * 4 + 16 * 4 + 2 * 8 + TC_GROUPS * 8;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),

@@ -13,6 +13,12 @@ out = torch.empty_like(x); stats = torch.zeros(32, 2, 32, dtype=torch.float64, d
 a = XmConvArgs(); a.g = g; a.mode = 0; a.stat_mode = 1
 a.src1, a.w1, a.w1_task_stride, a.out, a.stats = x.data_ptr(), w.data_ptr(), 9216, out.data_ptr(), stats.data_ptr()
 for _ in range(2):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     _lib.check(lib.xm_conv(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), 'conv')
+    ev1.record()
     torch.cuda.synchronize()
-    print('---')
+    Q = 25 * (H + 1) * (H + 1)
+    tiles = (Q + 125) // 126
+    print('--- kernel %.1f us; %d tiles per task, %.1f per SM -> %.3f us per tile' % (
+        ev0.elapsed_time(ev1) * 1e3, tiles, 32 * tiles / 148.0, ev0.elapsed_time(ev1) * 1e3 / (32 * tiles / 148.0)))
