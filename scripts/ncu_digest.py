@@ -8,6 +8,7 @@ import re
 import sys
 
 raw, log, out = sys.argv[1:4]
+stamp = sys.argv[4] if len(sys.argv) > 4 else None        # e.g. the git SHA the capture was taken at
 rows = list(csv.reader(open(raw)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
@@ -76,6 +77,8 @@ if calls and all(nk is not None for _k, nk, _c in calls) and sum(nk for _k, nk, 
         f['per_call'][key] = {'dram_bytes': dram, 'calls_per_step': cps, 'kernels': names}
     traffic = {k: {'dram_bytes_per_launch': v['bytes'] / max(v['calls'], 1), 'calls_per_step': v['calls'],
                    'per_call': v['per_call']} for k, v in fams.items()}
+    if stamp:
+        traffic['_meta'] = {'captured_at': stamp, 'source': raw}
     with open(out + '_traffic.json', 'w') as f:
         json.dump(traffic, f, indent=1)
     print('wrote', out + '_traffic.json')
