@@ -187,13 +187,11 @@ int conv_img_try(const XmConvArgs* a, cudaStream_t stream) {
   k.splits = splits;
   if (a->stat_mode) XM_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)g.tasks * 2 * g.cout * sizeof(double), stream));
   dim3 grid(splits, g.tasks, cotiles);
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per call: the attribute is per device, and a process may drive several
     XM_CUDA(cudaFuncSetAttribute(conv_img_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     XM_CUDA(cudaFuncSetAttribute(conv_img_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     XM_CUDA(cudaFuncSetAttribute(conv_img_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     XM_CUDA(cudaFuncSetAttribute(conv_img_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
   }
   switch (g.cin) {
     case 1: conv_img_kernel<1><<<grid, CI_THREADS, smem, stream>>>(k); break;

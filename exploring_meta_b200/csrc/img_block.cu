@@ -618,8 +618,7 @@ static int launch_gram(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
   const size_t smem = ((size_t)CIN * (GR_ROWS + 2) * (g.win + 2) + NPAIR * 9 + RG * 3) * sizeof(double);
   XM_REQUIRE(smem <= 200 * 1024, "xm_img_gram: image too wide");
-  static bool attr = false;
-  if (!attr) { XM_CUDA(cudaFuncSetAttribute(img_gram_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  XM_CUDA(cudaFuncSetAttribute(img_gram_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int nbands = g.n * ((g.hin + GR_ROWS - 1) / GR_ROWS);
   int splits = wave_ctas((const void*)img_gram_kernel<CIN>, threads, smem) / g.tasks;
   if (splits > nbands) splits = nbands;
@@ -637,8 +636,7 @@ static int launch_fwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   const size_t smem = ((size_t)K * 8 + 2 * ((size_t)(IB_ROWS + 2) * (g.win + 2) + 8)) * 16 + (size_t)2 * K * 32 * 4 +
                       ((size_t)K * K + K + 8 * 4 * 32) * 8 + 8 * 32 * 4;
   XM_REQUIRE(smem <= 200 * 1024, "xm_img_fwd: image too wide");
-  static bool attr = false;
-  if (!attr) { XM_CUDA(cudaFuncSetAttribute(img_fwd_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  XM_CUDA(cudaFuncSetAttribute(img_fwd_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int cotiles = g.cout / 32, nbands = g.n * ((g.hin + IB_ROWS - 1) / IB_ROWS);
   int splits = wave_ctas((const void*)img_fwd_kernel<CIN, DUAL>, IB_THREADS, smem) / (g.tasks * cotiles);
   if (splits > nbands) splits = nbands;
@@ -658,8 +656,7 @@ static int launch_bwd(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   const size_t band_fl = (size_t)CIN * (2 * IB_PROWS + 2) * (g.win + 2) + 8;
   const size_t smem = ((2 * band_fl + 1) & ~(size_t)1) * 4 + (size_t)(IB_THREADS / 32) * NA * 32 * 8;
   XM_REQUIRE(smem <= 200 * 1024, "xm_img_bwd: image too wide");
-  static bool attr = false;
-  if (!attr) { XM_CUDA(cudaFuncSetAttribute(img_bwd_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  XM_CUDA(cudaFuncSetAttribute(img_bwd_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int cotiles = g.cout / 32, nbands = g.n * ((g.hp + IB_PROWS - 1) / IB_PROWS);
   int splits = wave_ctas((const void*)img_bwd_kernel<CIN, DUAL>, IB_THREADS, smem) / (g.tasks * cotiles);
   if (splits > nbands) splits = nbands;
@@ -677,8 +674,7 @@ static int launch_finalize(const XmImgArgs* a, ImgK& k, cudaStream_t stream) {
   const XmBlockGeom& g = a->g;
   const size_t fsmem = ((size_t)K * K + K + (size_t)(DUAL ? 4 : 2) * g.cout * K) * sizeof(double);
   XM_REQUIRE(fsmem <= 200 * 1024, "xm_img_bwd: too many channels for the finalize kernel");
-  static bool fattr = false;
-  if (!fattr) { XM_CUDA(cudaFuncSetAttribute(img_finalize_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); fattr = true; }
+  XM_CUDA(cudaFuncSetAttribute(img_finalize_kernel<CIN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   img_finalize_kernel<CIN, DUAL><<<g.tasks, 256, fsmem, stream>>>(k);
   return launched(DUAL ? "xm_img_dual_bwd(finalize)" : "xm_img_bwd(finalize)");
 }

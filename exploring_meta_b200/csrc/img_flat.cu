@@ -268,8 +268,7 @@ template <int MODE>
 static int flat_launch_mode(const XmImgArgs* a, ImgK& k, cudaStream_t stream, const char* what) {
   const XmBlockGeom& g = a->g;
   const size_t smem = flat_smem(g);
-  static bool attr = false;
-  if (!attr) { XM_CUDA(cudaFuncSetAttribute(flat_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  XM_CUDA(cudaFuncSetAttribute(flat_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   int per_task = wave_ctas((const void*)flat_kernel<MODE>, FL_THREADS, smem) / g.tasks;
   if (per_task > g.n) per_task = g.n;
   if (per_task < 1) per_task = 1;

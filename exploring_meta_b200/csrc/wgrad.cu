@@ -430,11 +430,7 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
                "xm_wgrad: partial buffer too small");
     const size_t smem = wgrad_img_smem(g);
     XM_REQUIRE(smem <= 200 * 1024, "xm_wgrad: image too wide");
-    static bool attr_set = false;
-    if (!attr_set) {
-      XM_CUDA(cudaFuncSetAttribute(wgrad_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    XM_CUDA(cudaFuncSetAttribute(wgrad_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(k.splits, g.tasks, (g.cout + 31) / 32);
     wgrad_img_kernel<<<grid, WI_THREADS, smem, stream>>>(k);
     if (int rc = launched("xm_wgrad(image)")) return rc;

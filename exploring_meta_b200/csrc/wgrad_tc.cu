@@ -301,11 +301,9 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   p.npairs = a->x2 ? 2 : 1;
   p.x[0] = a->x1; p.g[0] = a->g1; p.x[1] = a->x2; p.g[1] = a->g2;
   p.partial = a->partial;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
   }
   // block (cb, ib) of a wide layer: gW[32 cb .. +31][32 ib .. +31] from g's channel block cb and x's channel block ib,
   // into partial region cb * blocks + ib

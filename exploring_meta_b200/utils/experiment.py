@@ -8,6 +8,15 @@ import os
 
 import numpy as np
 import torch
+import torch.distributed as dist
+
+
+def _writer():
+    """Under torchrun only rank 0 creates result directories and writes checkpoints / logs (every rank holds the same
+    parameters: replicated Adam on identical sums)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank() == 0
+    return int(os.environ.get('RANK', '0')) == 0
 
 
 class Experiment:
@@ -24,10 +33,13 @@ class Experiment:
         if path and not os.path.exists(path):
             os.makedirs(path, exist_ok=True)
         self.model_path = path + algo + '_' + dataset + '_' + self.logger['date'] + '_' + self.logger['model_id']
-        os.makedirs(self.model_path + '/model_checkpoints', exist_ok=True)
+        if _writer():
+            os.makedirs(self.model_path + '/model_checkpoints', exist_ok=True)
         self._use_wandb = False
 
     def log_model(self, model, device, input_shape=None, name='model'):
+        if not _writer():
+            return
         info = str(model)
         with open(self.model_path + '/' + name + '.summary', 'w') as file:
             file.write(info)
@@ -37,6 +49,8 @@ class Experiment:
             self.metrics.setdefault(key, []).append(value)
 
     def save_logs_to_file(self):
+        if not _writer():
+            return
         print('Saving metrics...')
         with open(self.model_path + '/metrics.json', 'w') as fp:
             json.dump(self.metrics, fp)
@@ -45,6 +59,8 @@ class Experiment:
             json.dump(self.logger, fp, sort_keys=True, indent=4)
 
     def save_model(self, model, name='model'):
+        if not _writer():
+            return
         print('Saving ' + name + '...')
         torch.save(model.state_dict(), self.model_path + '/' + name + '.pt')
 
@@ -52,6 +68,8 @@ class Experiment:
         self.save_model(model, name='/model_checkpoints/model_' + epoch)
 
     def save_acc_matrix(self, acc_matrix):
+        if not _writer():
+            return
         print('Saving accuracy matrix..')
         print(acc_matrix)
         np.savetxt(self.model_path + '/acc_matrix.out', acc_matrix, fmt='%1.2f')

@@ -76,7 +76,15 @@ class AnilVision(Experiment):
             print("Dataset not supported")
             raise SystemExit(2)
         if tasks is None:
+            # The reference's learn2learn dataset builders (utils/data_pre.py:16-112) need a download and are not
+            # re-implemented: without caller-supplied task objects the run is on SYNTHETIC tasks, and says so.
+            print('WARNING: no task datasets given -- training on synthetic %s-shaped tasks '
+                  '(exploring_meta_b200.synthetic.get_tasks); pass tasks=(train, valid, test) objects with .sample() '
+                  'for real data' % dataset, flush=True)
+            self.logger['data'] = self.params['data'] = 'synthetic'
             tasks = get_tasks(dataset, self.params['ways'], self.params['shots'], seed=self.params['seed'] + 7919 * rank)
+        else:
+            self.logger['data'] = self.params['data'] = 'caller-supplied task datasets'
         if run:
             self.run(tasks[0], tasks[1], tasks[2], input_shape, device)
 
@@ -173,7 +181,12 @@ class AnilVision(Experiment):
         self.save_model(features, name='features')
         self.save_model(head, name='head')
         self.logger['elapsed_time'] = str(round(time.time() - t0, 2)) + ' sec'
-        self.logger['test_acc'] = evaluate(self.params, test_tasks, head, loss, device, features=features)
+        test_acc = evaluate(self.params, test_tasks, head, loss, device, features=features)
+        if dist.is_initialized() and dist.get_world_size() > 1:        # every rank evaluated its own test tasks
+            acc = torch.tensor([test_acc], dtype=torch.float64, device=device)
+            dist.all_reduce(acc)
+            test_acc = float(acc.item()) / dist.get_world_size()
+        self.logger['test_acc'] = test_acc
         self.log_metrics({'test_acc': self.logger['test_acc']})
         self.save_logs_to_file()
 

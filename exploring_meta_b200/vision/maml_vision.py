@@ -133,7 +133,15 @@ class MamlVision(Experiment):
             print("Dataset not supported")
             raise SystemExit(2)
         if tasks is None:
+            # The reference's learn2learn dataset builders (utils/data_pre.py:16-112) need a download and are not
+            # re-implemented: without caller-supplied task objects the run is on SYNTHETIC tasks, and says so.
+            print('WARNING: no task datasets given -- training on synthetic %s-shaped tasks '
+                  '(exploring_meta_b200.synthetic.get_tasks); pass tasks=(train, valid, test) objects with .sample() '
+                  'for real data' % dataset, flush=True)
+            self.logger['data'] = self.params['data'] = 'synthetic'
             tasks = get_tasks(dataset, self.params['ways'], self.params['shots'], seed=self.params['seed'] + 7919 * rank)
+        else:
+            self.logger['data'] = self.params['data'] = 'caller-supplied task datasets'
         self.model = model
         if run:
             self.run(tasks[0], tasks[1], tasks[2], model, input_shape, device)
@@ -194,7 +202,12 @@ class MamlVision(Experiment):
         write_back()
         self.save_model(model)
         self.logger['elapsed_time'] = str(round(time.time() - t0, 2)) + ' sec'
-        self.logger['test_acc'] = evaluate(self.params, test_tasks, maml, loss, device)
+        test_acc = evaluate(self.params, test_tasks, maml, loss, device)
+        if dist.is_initialized() and dist.get_world_size() > 1:        # every rank evaluated its own test tasks
+            acc = torch.tensor([test_acc], dtype=torch.float64, device=device)
+            dist.all_reduce(acc)
+            test_acc = float(acc.item()) / dist.get_world_size()
+        self.logger['test_acc'] = test_acc
         self.log_metrics({'test_acc': self.logger['test_acc']})
         self.save_logs_to_file()
 
