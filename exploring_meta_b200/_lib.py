@@ -130,7 +130,7 @@ class XmRlSweepArgs(Structure):
                 ('out', c_void_p), ('out_task_stride', c_int64),
                 ('base', c_void_p), ('base_task_stride', c_int64), ('scale', c_float),
                 ('task_loss', c_void_p), ('task_kl', c_void_p), ('mu_out', c_void_p),
-                ('partial', c_void_p), ('partial_bytes', c_int64)]
+                ('partial', c_void_p), ('partial_bytes', c_int64), ('clip', c_float), ('head_only', c_int32)]
 
 
 XM_RL_A2C, XM_RL_SURROGATE, XM_RL_FISHER = 0, 1, 2

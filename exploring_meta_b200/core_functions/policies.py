@@ -73,6 +73,57 @@ class DiagNormalPolicy(nn.Module):
         return self
 
 
+class DiagNormalPolicyANIL(nn.Module):
+    """policies.py:70-126: the same network split into ``body`` (all layers but the last) and ``head``; during the inner
+    loop the body runs under no_grad (``turn_off_body_grads``), so only ``sigma`` and the head adapt.  Same flat
+    parameter layout as ``DiagNormalPolicy`` (sigma, body.0, body.2, head)."""
+
+    def __init__(self, input_size, output_size, fc_neurons, hiddens=None):
+        super().__init__()
+        if hiddens is None:
+            hiddens = [100, 100]
+        self.activation = 'tanh'
+        self.fc_neurons = fc_neurons
+        layers = [linear_init(nn.Linear(input_size, hiddens[0])), nn.Tanh()]
+        for i, o in zip(hiddens[:-1], hiddens[1:]):
+            layers.append(linear_init(nn.Linear(i, o)))
+            layers.append(nn.Tanh())
+        self.body = nn.Sequential(*layers)
+        self.head = linear_init(nn.Linear(fc_neurons, output_size))
+        self.sigma = nn.Parameter(torch.Tensor(output_size))
+        self.sigma.data.fill_(math.log(1))
+        self.features_no_grad = False
+        self.input_size, self.output_size, self.hiddens = input_size, output_size, list(hiddens)
+
+    def turn_on_body_grads(self):
+        self.features_no_grad = False
+
+    def turn_off_body_grads(self):
+        self.features_no_grad = True
+
+    def forward_pass(self, state):
+        if self.features_no_grad:
+            with torch.no_grad():
+                state_features = self.body(state)
+        else:
+            state_features = self.body(state)
+        return self.head(state_features)
+
+    def density(self, state):
+        loc = self.forward_pass(state)
+        scale = torch.exp(torch.clamp(self.sigma, min=math.log(EPSILON)))
+        return Normal(loc=loc, scale=scale)
+
+    def log_prob(self, state, action):
+        return self.density(state).log_prob(action).mean(dim=1, keepdim=True)
+
+    def forward(self, state):
+        return self.density(state).sample()
+
+    flat_parameters = DiagNormalPolicy.flat_parameters
+    load_flat_parameters = DiagNormalPolicy.load_flat_parameters
+
+
 class LinearValue(nn.Module):
     """Mirror of ``cherry.models.robotics.LinearValue`` (the baseline the reference passes around,
     rl/maml_trpo.py:85): ridge regression on [s, s^2, t, t^2, t^3, 1].  Inside the kernels the fit is part of

@@ -3,6 +3,7 @@ argument order and side effects, running on libxmeta's kernels through ``rl_engi
 
   compute_advantages   rl.py:95-110     trpo_a2c_loss        rl.py:346-358     trpo_update   rl.py:361-374
   fast_adapt_trpo      rl.py:377-406    meta_surrogate_loss  rl.py:441-473     meta_optimize_trpo   rl.py:409-438
+  fast_adapt_ppo       rl.py:264-316 (MAML-PPO and, with ``anil=True`` + ``DiagNormalPolicyANIL``, ANIL-PPO)
 
 ``episodes`` / replays are anything with cherry's ExperienceReplay accessors (``state() action() reward() done()
 next_state()``) or dicts with the plural keys.  Losses are returned as detached device scalars: the second-order
@@ -133,3 +134,61 @@ def meta_optimize_trpo(params, policy, baseline, iter_replays, iter_policies, an
                                 params['outer_lr'])
     policy.load_flat_parameters(new)
     return diag
+
+
+
+class _PpoValidLoss(torch.autograd.Function):
+    """The validation loss of ``fast_adapt_ppo`` as a function of the learner's (cloned, pre-adaptation) parameters:
+    the value and its second-order gradient were computed by the kernels; ``backward`` hands the gradient to autograd,
+    which carries it through the ``clone()`` edges into the master policy's ``.grad`` (rl/maml_ppo.py:129)."""
+
+    @staticmethod
+    def forward(ctx, value, grad_flat, *params):
+        ctx.grad_flat, ctx.shapes = grad_flat, [p.shape for p in params]
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        outs, o = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            outs.append((gout * ctx.grad_flat[o:o + n]).view(shp))
+            o += n
+        return (None, None) + tuple(outs)
+
+
+def fast_adapt_ppo(task, learner, baseline, params, anil=False, render=False):
+    """rl.py:264-316.  ``learner`` = ``policy.clone()`` of a ``MAML``-wrapped ``DiagNormalPolicy`` /
+    ``DiagNormalPolicyANIL``; ``task.run(learner, episodes=...)`` collects the replays (environment side,
+    caller-provided).  Returns ``(valid_loss, query_rew, query_success_rate)``; ``valid_loss.backward()`` accumulates
+    the second-order meta-gradient into the master policy like the reference's autograd graph does."""
+    if params.get('adapt_steps', 1) != 1:
+        raise NotImplementedError('one adaptation step (one support replay) per task')
+    policy = learner.module
+    before = list(policy.parameters())                       # the clone's differentiable copies of the master
+    dev = before[0].device
+    theta0 = torch.cat([p.detach().reshape(-1).float() for p in before])
+    if anil:
+        policy.turn_off_body_grads()
+    support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
+    e = _engine(policy, baseline, 1, support['states'].shape[0], params['inner_lr'], params['gamma'], params['tau'], dev)
+    e.load_replays([[support, support]])
+    adapted = e.ppo_adapt(theta0, params['ppo_epochs'], params['ppo_clip_ratio'], anil)[0].clone()
+    # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the query rollouts
+    o = 0
+    for module in policy.modules():
+        for name, p in list(module._parameters.items()):
+            if p is not None:
+                module._parameters[name] = adapted[o:o + p.numel()].view_as(p)
+                o += p.numel()
+    if anil:
+        policy.turn_on_body_grads()
+    query_episodes = task.run(learner, episodes=params['adapt_batch_size'])
+    query = _as_dict(query_episodes)
+    e.load_replays([[support, query]])
+    valid, grad = e.ppo_outer(params['ppo_epochs'], params['ppo_clip_ratio'], anil)
+    valid_loss = _PpoValidLoss.apply(valid[0], grad, *before)
+    query_rew = query['rewards'].sum().item() / params['adapt_batch_size']
+    return valid_loss, query_rew, 0.0

@@ -210,7 +210,8 @@ constexpr float HALF_LOG_2PI = 0.9189385332046727f;
 struct SweepK {
   int n, in, out, h1, h2, act, loss, what, G;
   const float* states; const float* actions; const float* coef; const float* mu_old; const float* logstd_old;
-  float kl_scale;
+  float kl_scale, clip;
+  int head_only;
   const float* theta; long long theta_stride;
   const float* theta_dot; long long dot_stride;
   float* mu_out;
@@ -257,14 +258,15 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
   const float* thd = DF ? k.theta_dot + (long long)task * k.dot_stride : nullptr;
   const int oW1 = OUT, ob1 = oW1 + H1 * IN, oW2 = ob1 + H1, ob2 = oW2 + H2 * H1, oW3 = ob2 + H2, ob3 = oW3 + OUT * H2;
   for (int i = tid; i < OUT; i += RL_THREADS) { sig[i] = th[i]; b3[i] = th[ob3 + i]; if (DF) { sigd[i] = thd[i]; b3d[i] = thd[ob3 + i]; } }
-  for (int i = tid; i < H1 * IN; i += RL_THREADS) { W1[i] = th[oW1 + i]; if (DF) W1d[i] = thd[oW1 + i]; }
-  for (int i = tid; i < H1; i += RL_THREADS) { b1[i] = th[ob1 + i]; if (DF) b1d[i] = thd[ob1 + i]; }
-  for (int i = tid; i < H2; i += RL_THREADS) { b2[i] = th[ob2 + i]; if (DF) b2d[i] = thd[ob2 + i]; }
+  const bool body_dot = !(k.head_only & 2);             // ANIL cotangent: the body entries of the direction are masked out
+  for (int i = tid; i < H1 * IN; i += RL_THREADS) { W1[i] = th[oW1 + i]; if (DF) W1d[i] = body_dot ? thd[oW1 + i] : 0.f; }
+  for (int i = tid; i < H1; i += RL_THREADS) { b1[i] = th[ob1 + i]; if (DF) b1d[i] = body_dot ? thd[ob1 + i] : 0.f; }
+  for (int i = tid; i < H2; i += RL_THREADS) { b2[i] = th[ob2 + i]; if (DF) b2d[i] = body_dot ? thd[ob2 + i] : 0.f; }
   for (int i = tid; i < OUT * H2; i += RL_THREADS) { W3[i] = th[oW3 + i]; if (DF) W3d[i] = thd[oW3 + i]; }
   for (int i = tid; i < H2 * H1; i += RL_THREADS) {
     const int r = i / H1, c = i - r * H1;
     W2[r * ldw + c] = th[oW2 + i];
-    if (DF) W2d[r * ldw + c] = thd[oW2 + i];
+    if (DF) W2d[r * ldw + c] = body_dot ? thd[oW2 + i] : 0.f;
   }
   __syncthreads();
   if (tid < OUT) {
@@ -391,13 +393,27 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
       }
       lp *= invA;
       lpo *= invA;
-      float wgt = c;                                   // d l / d lp
+      float wgt = c, wgtd = 0.f;                       // d l / d lp and its tangent
       if (k.loss == XM_RL_A2C) {
         if (ok) loss_acc += (double)(c * lp);
       } else if (k.loss == XM_RL_SURROGATE) {
         const float ratio = expf(lp - lpo);
         wgt = c * ratio;
-        if (ok) { loss_acc += (double)wgt; kl_acc += (double)k.kl_scale * klv; }
+        float val = wgt;
+        if (k.clip > 0.f) {                            // PPO: max(c r, c clamp(r)); the clamped branch has no gradient
+          const float rc = fminf(fmaxf(ratio, 1.f - k.clip), 1.f + k.clip);
+          const bool inside = ratio >= 1.f - k.clip && ratio <= 1.f + k.clip;
+          if (!inside && c * ratio <= c * rc) { wgt = 0.f; val = c * rc; }
+        }
+        if (ok) { loss_acc += (double)val; kl_acc += (double)k.kl_scale * klv; }
+        if (DB) {                                      // tangent of the weight: d(c r)/d eps = c r * lp_dot
+          float lpd = 0.f;
+          for (int d = 0; d < OUT; ++d) {
+            const float e = ACT[s * OUT + d] - MU[s * OUT + d], is2 = expf(-2.f * lam[d]);
+            lpd += invA * (e * is2 * MUD[s * OUT + d] + (e * e * is2 - 1.f) * lamd[d]);
+          }
+          wgtd = wgt * lpd;
+        }
       }
 #pragma unroll
       for (int d = 0; d < RL_MAXIO; ++d) {
@@ -411,10 +427,10 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
           gm = wgt * invA * e * is2;
           if (!DB) {
             accls[d] += wgt * invA * (e * e * is2 - 1.f);
-          } else {                                     // tangent of the A2C gradient terms (Hessian-vector product)
+          } else {                                     // tangent of the gradient terms (Hessian-vector product)
             const float mud = MUD[s * OUT + d];
-            gmd = c * invA * is2 * (-mud - 2.f * e * lamd[d]);
-            accls[d] += c * invA * is2 * (-2.f * e * mud - 2.f * e * e * lamd[d]);
+            gmd = wgtd * invA * e * is2 + wgt * invA * is2 * (-mud - 2.f * e * lamd[d]);
+            accls[d] += wgtd * invA * (e * e * is2 - 1.f) + wgt * invA * is2 * (-2.f * e * mud - 2.f * e * e * lamd[d]);
           }
         }
         GMU[s * OUT + d] = gm;
@@ -580,7 +596,7 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
 // out[t][p] = (base ? base[t][p] : 0) + scale * sum_g partial[t][g][p]   (fixed order); block (0, t) also reduces the
 // scalars.
 __global__ void rl_reduce_kernel(const float* __restrict__ partial, const double* __restrict__ partial_sc, int G, int P,
-                                 int reduce_vec, float* __restrict__ out, long long out_stride,
+                                 int reduce_vec, int body_lo, int body_hi, float* __restrict__ out, long long out_stride,
                                  const float* __restrict__ base, long long base_stride, float scale,
                                  float* __restrict__ task_loss, float* __restrict__ task_kl) {
   const int task = blockIdx.y;
@@ -588,6 +604,7 @@ __global__ void rl_reduce_kernel(const float* __restrict__ partial, const double
   if (reduce_vec && pidx < P) {
     float acc = 0.f;
     for (int g = 0; g < G; ++g) acc += partial[((long long)task * G + g) * P + pidx];
+    if (pidx >= body_lo && pidx < body_hi) acc = 0.f;          // ANIL: the body does not adapt in the inner loop
     const float b = base ? base[(long long)task * base_stride + pidx] : 0.f;
     out[(long long)task * out_stride + pidx] = b + scale * acc;
   }
@@ -645,7 +662,8 @@ extern "C" int xm_rl_sweep(const XmRlSweepArgs* a, void* stream_) {
   if (int rc = sweep_check(a)) return rc;
   XM_REQUIRE(a->states && a->theta && a->partial, "xm_rl_sweep: null states / theta / partial");
   const bool hvp = a->what == XM_RL_HVP, fisher = a->loss == XM_RL_FISHER;
-  XM_REQUIRE(!hvp || a->loss == XM_RL_A2C, "xm_rl_sweep: XM_RL_HVP is defined for XM_RL_A2C");
+  XM_REQUIRE(!hvp || a->loss != XM_RL_FISHER, "xm_rl_sweep: XM_RL_HVP is defined for XM_RL_A2C / XM_RL_SURROGATE");
+  XM_REQUIRE(a->clip >= 0.f && a->clip < 1.f, "xm_rl_sweep: bad clip");
   XM_REQUIRE(!(hvp || fisher) || a->theta_dot, "xm_rl_sweep: theta_dot required");
   XM_REQUIRE(!fisher || a->what == XM_RL_GRAD, "xm_rl_sweep: XM_RL_FISHER produces a gradient");
   XM_REQUIRE(a->loss == XM_RL_FISHER || a->what == XM_RL_FORWARD || (a->actions && a->coef),
@@ -660,7 +678,7 @@ extern "C" int xm_rl_sweep(const XmRlSweepArgs* a, void* stream_) {
   k.loss = a->loss; k.what = a->what;
   k.G = sweep_ctas_per_task(a->tasks, a->n);
   k.states = a->states; k.actions = a->actions; k.coef = a->coef; k.mu_old = a->mu_old; k.logstd_old = a->logstd_old;
-  k.kl_scale = a->kl_scale;
+  k.kl_scale = a->kl_scale; k.clip = a->clip; k.head_only = a->head_only;
   k.theta = a->theta; k.theta_stride = a->theta_task_stride;
   k.theta_dot = a->theta_dot; k.dot_stride = a->theta_dot_task_stride;
   k.mu_out = a->mu_out;
@@ -692,7 +710,9 @@ extern "C" int xm_rl_sweep(const XmRlSweepArgs* a, void* stream_) {
   if (int rc = launched("xm_rl_sweep")) return rc;
   const int reduce_vec = a->what != XM_RL_FORWARD;
   dim3 rgrid(reduce_vec ? (k.P + 255) / 256 : 1, a->tasks);
-  rl_reduce_kernel<<<rgrid, 256, 0, stream>>>(k.partial, k.partial_sc, k.G, k.P, reduce_vec, a->out, a->out_task_stride,
+  const int body_lo = (a->head_only & 1) ? a->out_dim : 0;
+  const int body_hi = (a->head_only & 1) ? a->out_dim + a->h1 * a->in_dim + a->h1 + a->h2 * a->h1 + a->h2 : 0;
+  rl_reduce_kernel<<<rgrid, 256, 0, stream>>>(k.partial, k.partial_sc, k.G, k.P, reduce_vec, body_lo, body_hi, a->out, a->out_task_stride,
                                               a->base, a->base_task_stride, a->scale, a->task_loss, a->task_kl);
   return launched("xm_rl_sweep(reduce)");
 }

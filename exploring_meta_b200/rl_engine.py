@@ -171,6 +171,68 @@ class TrpoEngine:
         self._launch(a)
         return out
 
+    # ---- MAML / ANIL - PPO inner loop (core_functions/rl.py:264-316) ---------------------------------------------------------
+    def _ppo_args(self, what, e, clip):
+        a = self._sweep_args(XM_RL_SURROGATE, what, 0)
+        a.theta, a.theta_task_stride = _p(self.ppo_thetas[e]), self.P
+        a.mu_old, a.logstd_old, a.clip = _p(self.mu_old_s), _p(self.logstd_old_s), clip
+        return a
+
+    def ppo_adapt(self, theta, epochs, clip, anil=False):
+        """The inner loop of ``fast_adapt_ppo`` (rl.py:268-293) for every task: ``epochs`` steps
+        theta_{e+1} = theta_e - lr * M grad L_ppo(theta_e) on the support replay, old log-probabilities fixed at theta_0
+        (no_grad, :281-282), M = identity (MAML) or the head / sigma mask (ANIL: the body runs under no_grad and
+        ``allow_unused`` skips its update).  Returns the adapted parameters [tasks, P]."""
+        B, P = self.tasks, self.P
+        if getattr(self, 'ppo_thetas', None) is None or self.ppo_thetas.shape[0] != epochs + 1:
+            self.ppo_thetas = torch.zeros(epochs + 1, B, P, dtype=torch.float32, device=self.device)
+            self.mu_old_s = torch.zeros(B, self.n, self.ad, dtype=torch.float32, device=self.device)
+            self.logstd_old_s = torch.zeros(B, self.ad, dtype=torch.float32, device=self.device)
+        th = self.ppo_thetas
+        th[0].copy_(theta.expand(B, P) if theta.dim() == 1 else theta)
+        a = self._sweep_args(XM_RL_A2C, XM_RL_FORWARD, 0)          # old policy outputs on the support states
+        a.theta, a.theta_task_stride, a.mu_out = _p(th[0]), P, _p(self.mu_old_s)
+        self._launch(a)
+        self.logstd_old_s.copy_(torch.clamp(th[0][:, :self.ad], min=LOG_EPS))
+        for e in range(epochs):
+            a = self._ppo_args(XM_RL_GRAD, e, clip)
+            a.out, a.out_task_stride = _p(th[e + 1]), P
+            a.base, a.base_task_stride, a.scale = _p(th[e]), P, -self.lr
+            a.head_only = 1 if anil else 0
+            self._launch(a)
+        return th[epochs]
+
+    def ppo_outer(self, epochs, clip, anil=False):
+        """Validation loss of the adapted policies on the query replay (rl.py:297-309: the PPO objective against the
+        adapted policy's OWN detached log-probabilities -- the ratio is identically 1, so the value is sum(coef) and the
+        gradient is the a2c gradient at theta_E) and its second-order gradient w.r.t. theta_0:
+        bar_e = bar_{e+1} - lr * M H_e (M bar_{e+1}), H_e v = the tangent of the PPO gradient sweep at theta_e.
+        Returns (valid loss per task (already / total tasks), sum over tasks of the gradient [P])."""
+        P = self.P
+        a = self._sweep_args(XM_RL_A2C, XM_RL_GRAD, 1)
+        a.theta, a.theta_task_stride = _p(self.ppo_thetas[epochs]), P
+        a.out, a.out_task_stride, a.scale = _p(self.bar), P, 1.0
+        self._launch(a)
+        valid_loss = self.coef[1].sum(dim=1)
+        cur, nxt = self.bar, self.pertask
+        for e in reversed(range(epochs)):
+            a = self._ppo_args(XM_RL_HVP, e, clip)
+            a.theta_dot, a.theta_dot_task_stride = _p(cur), P
+            a.out, a.out_task_stride = _p(nxt), P
+            a.base, a.base_task_stride, a.scale = _p(cur), P, -self.lr
+            a.head_only = 3 if anil else 0          # the inner-loop graph holds the head / sigma only (body under no_grad)
+            self._launch(a)
+            cur, nxt = nxt, cur
+        self.ppo_task_grads = cur
+        return valid_loss, self._sum_tasks(cur)
+
+    def ppo_meta_gradient(self, theta, epochs, clip, anil=False):
+        """``fast_adapt_ppo`` for every task + the gradient of the mean validation loss (rl/maml_ppo.py:103-129,
+        rl/anil_ppo.py:106-130).  Returns (valid loss per task, gradient [P], adapted parameters [tasks, P])."""
+        adapted = self.ppo_adapt(theta, epochs, clip, anil)
+        valid, grad = self.ppo_outer(epochs, clip, anil)
+        return valid, grad, adapted
+
     def _sum_tasks(self, per_task):
         out = torch.empty(self.P, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.xm_accumulate_tasks(_p(per_task), self.P, self.tasks, self.P, _p(out), 0, self._stream()),

@@ -325,13 +325,19 @@ int xm_rl_advantages(const XmRlAdvArgs* a, void* stream);
 /* xm_rl_sweep: one pass of every task's policy over its n transitions, per-task parameters (theta + t*stride).
  *   loss XM_RL_A2C       l = sum_n coef[n] * log_prob(a_n | s_n)                     (trpo_a2c_loss, rl.py:346-358)
  *        XM_RL_SURROGATE l = sum_n coef[n] * exp(log_prob_new - log_prob_old),  kl = mean KL(new || old)/tasks_total
- *                        with the old policy given by its means mu_old[n][out] and log-std (rl.py:459-469)
+ *                        with the old policy given by its means mu_old[n][out] and log-std (rl.py:459-469).
+ *                        clip > 0: the PPO objective of fast_adapt_ppo (rl.py:264-316, ch.algorithms.ppo.policy_loss):
+ *                        l = sum_n max(coef[n] * r, coef[n] * clamp(r, 1 - clip, 1 + clip)), r the probability ratio
  *        XM_RL_FISHER    the Gauss-Newton factor of that KL at new == old: the output cotangent is
  *                        F * (tangent of the outputs in direction theta_dot), F = diag(1/sigma_old^2, 2) * kl_scale
  *   what XM_RL_FORWARD   values only (task_loss / task_kl, optional mu_out): the line search of rl.py:429-438
  *        XM_RL_GRAD      d l / d theta                          (theta_dot: only for XM_RL_FISHER, where it is required)
- *        XM_RL_HVP       d/d eps [ d l / d theta ](theta + eps * theta_dot)   (XM_RL_A2C only): the Hessian-vector
- *                        product of the inner loss = what create_graph=True back-propagates through (rl.py:368-374)
+ *        XM_RL_HVP       d/d eps [ d l / d theta ](theta + eps * theta_dot)   (XM_RL_A2C, XM_RL_SURROGATE): the Hessian-
+ *                        vector product of the inner loss = what create_graph=True back-propagates through
+ *                        (rl.py:368-374; learner.adapt(loss) at :291 for the PPO inner loop)
+ * head_only (the ANIL policy, policies.py:70-126: the body is frozen in the inner loop, `turn_off_body_grads`):
+ *   bit 0: the body entries (W1, b1, W2, b2) of the RESULT are zeroed before the epilogue (theta' = theta - lr * M g);
+ *   bit 1: the body entries of theta_dot are zeroed on load (cotangent v - lr * H (M v)).
  * Result r [P] per task through the axpy epilogue out = (base ? base : 0) + scale * r  (maml_update fused:
  * theta' = theta - inner_lr * grad; cotangent recursion v - inner_lr * H v).  Deterministic: per-CTA partial sums in
  * `partial` (xm_rl_sweep_scratch_bytes), reduced in a fixed order. */
@@ -351,6 +357,8 @@ typedef struct XmRlSweepArgs {
   float* task_loss; float* task_kl;                           /* optional [tasks]                        */
   float* mu_out;                                              /* optional [tasks][n][out_dim]            */
   float* partial; int64_t partial_bytes;
+  float clip;                                                 /* PPO clip ratio (0: unclipped surrogate)  */
+  int32_t head_only;                                          /* ANIL masks, see above                   */
 } XmRlSweepArgs;
 int64_t xm_rl_sweep_scratch_bytes(const XmRlSweepArgs* a);
 int xm_rl_sweep(const XmRlSweepArgs* a, void* stream);

@@ -8,6 +8,7 @@ Follows, function by function:
   core_functions/rl.py:361-374       trpo_update    (inner step theta' = theta - lr * grad, first or second order)
   core_functions/rl.py:441-473       meta_surrogate_loss (re-adaptation on the stored support replays, KL(new || old),
                                      importance-weighted surrogate on the query replay; means over tasks)
+  core_functions/rl.py:264-316       fast_adapt_ppo (PPO inner loop of MAML / ANIL - PPO, policies.py:70-126 for the ANIL policy)
   core_functions/rl.py:409-438       meta_optimize_trpo (gradient, Fisher-vector product of the KL, conjugate gradient,
                                      step scaling by max_kl, backtracking line search)
 plus the cherry functions restated in oracle/cherry_shim.py.  Parameters are a flat list in
@@ -83,6 +84,48 @@ def trpo_update(params, rep, inner_lr, tau, gamma, value_reg, first_order=False)
     loss = a2c_loss(params, rep, tau, gamma, value_reg)
     grads = torch.autograd.grad(loss, params, retain_graph=not first_order, create_graph=not first_order)
     return [p - inner_lr * g for p, g in zip(params, grads)]
+
+
+def policy_mean_anil(params, states, activation=torch.tanh, body_no_grad=False):
+    """DiagNormalPolicyANIL.forward_pass (policies.py:98-104): body = all layers but the last, head = the last Linear;
+    with ``features_no_grad`` the body runs under no_grad."""
+    n_lin = (len(params) - 1) // 2
+    def body(h):
+        for l in range(n_lin - 1):
+            h = activation(h @ params[1 + 2 * l].t() + params[2 + 2 * l])
+        return h
+    if body_no_grad:
+        with torch.no_grad():
+            feats = body(states)
+    else:
+        feats = body(states)
+    return feats @ params[2 * n_lin - 1].t() + params[2 * n_lin]
+
+
+def fast_adapt_ppo(params, support, query, cfg, anil=False, activation=torch.tanh):
+    """core_functions/rl.py:264-316 on fixed replays (the environment rollouts replaced by ``support`` / ``query``):
+    ``ppo_epochs`` inner steps of learn2learn ``adapt`` (second order) on the clipped PPO objective with the old
+    log-probabilities fixed at the un-adapted learner, then the PPO objective of the adapted learner on the query
+    replay against its own detached log-probabilities.  ANIL: the body runs under no_grad during the inner loop
+    (``turn_off_body_grads``) and ``allow_unused`` leaves its parameters un-adapted.  Returns (validation loss with
+    graph, adapted parameter list)."""
+    def lp(ps, rep, body_no_grad=False):
+        mean = policy_mean_anil(ps, rep['states'], activation, body_no_grad) if anil else policy_mean(ps, rep['states'], activation)
+        scale = torch.exp(torch.clamp(ps[0], min=math.log(EPSILON)))
+        return Normal(loc=mean, scale=scale).log_prob(rep['actions']).mean(dim=1, keepdim=True)
+    adv = ch.normalize(compute_advantages(support, cfg['tau'], cfg['gamma'], cfg['value_reg'])).detach()
+    with torch.no_grad():
+        old_lp = lp(params, support, anil)
+    new = list(params)
+    for _epoch in range(cfg['ppo_epochs']):
+        loss = ch.ppo_policy_loss(lp(new, support, anil), old_lp, adv, clip=cfg['ppo_clip_ratio'])
+        grads = torch.autograd.grad(loss, new, retain_graph=True, create_graph=True, allow_unused=anil)
+        new = [p if g is None else p - cfg['inner_lr'] * g for p, g in zip(new, grads)]
+    adv_q = ch.normalize(compute_advantages(query, cfg['tau'], cfg['gamma'], cfg['value_reg'])).detach()
+    with torch.no_grad():
+        old_q = lp(new, query)
+    valid = ch.ppo_policy_loss(lp(new, query), old_q, adv_q, clip=cfg['ppo_clip_ratio'])
+    return valid, new
 
 
 def meta_surrogate_loss(params, iter_replays, iter_old_params, cfg):

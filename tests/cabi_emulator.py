@@ -730,6 +730,9 @@ class EmulatedLib:
             act = view(a.actions + 4 * t * n * OUT, (n, OUT)).double() if a.actions else None
             coef = view(a.coef + 4 * t * n, (n,)).double() if a.coef else None
             thd = view(a.theta_dot + 4 * t * a.theta_dot_task_stride, (P,)).double().clone() if a.theta_dot else None
+            body = slice(OUT, OUT + H1 * IN + H1 + H2 * H1 + H2)
+            if thd is not None and (a.head_only & 2):
+                thd[body] = 0.0
             lamo = view(a.logstd_old + 4 * t * OUT, (OUT,)).double() if a.logstd_old else None
             muo = view(a.mu_old + 4 * t * n * OUT, (n, OUT)).double() if a.mu_old else None
 
@@ -742,7 +745,12 @@ class EmulatedLib:
                     return (coef * log_prob(mu, lam, act)).sum(), torch.zeros((), dtype=torch.float64)
                 lp, lpo = log_prob(mu, lam, act), log_prob(muo, lamo, act)
                 kl = (lamo - lam + (torch.exp(2 * lam) + (mu - muo) ** 2) / (2 * torch.exp(2 * lamo)) - 0.5).sum()
-                return (coef * torch.exp(lp - lpo)).sum(), a.kl_scale * kl
+                ratio = torch.exp(lp - lpo)
+                if a.clip > 0:          # ppo.policy_loss: -mean(min(r A, clamp(r) A)) with coef = -A / n
+                    val = torch.max(coef * ratio, coef * ratio.clamp(1.0 - a.clip, 1.0 + a.clip))
+                else:
+                    val = coef * ratio
+                return val.sum(), a.kl_scale * kl
 
             res, l, kl = None, None, None
             if a.loss == 2:                                         # Fisher factor J^T F J theta_dot
@@ -760,6 +768,9 @@ class EmulatedLib:
                 if a.mu_out:
                     view(a.mu_out + 4 * t * n * OUT, (n, OUT)).copy_(outputs(th0.detach(), x)[0].float())
             if res is not None:
+                if a.head_only & 1:
+                    res = res.clone()
+                    res[body] = 0.0
                 base = view(a.base + 4 * t * a.base_task_stride, (P,)).double() if a.base else torch.zeros(P, dtype=torch.float64)
                 view(a.out + 4 * t * a.out_task_stride, (P,)).copy_((base + a.scale * res).float())
             if a.task_loss and l is not None:

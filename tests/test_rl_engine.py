@@ -148,3 +148,66 @@ def test_reference_api_surface(kdev):
     diag = xrl.meta_optimize_trpo(params, policy, baseline, iter_replays, iter_policies)
     assert diag['ls_step'] == int(g['ls_step'])
     assert rel(policy.flat_parameters(), torch.from_numpy(g['theta1'])) < 1e-4
+
+
+GOLD_PPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'rl', 'rl_ppo_small.npz')
+PPO_CFG = {'inner_lr': 0.05, 'tau': 1.0, 'gamma': 0.99, 'value_reg': 2, 'ppo_epochs': 3, 'ppo_clip_ratio': 0.1}
+
+
+@pytest.mark.parametrize('anil', [False, True])
+def test_ppo_inner_loop_and_meta_gradient_match_reference_fixture(kdev, anil):
+    """MAML-PPO / ANIL-PPO: the reference's own fast_adapt_ppo + backward on fixed replays
+    (tests/golden/make_golden_ppo.py) against the task-batched kernels: adapted parameters after 3 clipped-PPO inner
+    steps, validation loss, and the second-order gradient of the mean validation loss w.r.t. the initial parameters."""
+    g = np.load(GOLD_PPO)
+    key = 'anil' if anil else 'maml'
+    tasks, n = int(g['tasks']), int(g['episodes']) * int(g['horizon'])
+    e = TrpoEngine(tasks, n, 2, 2, (100, 100), 'tanh', PPO_CFG['inner_lr'], PPO_CFG['gamma'], PPO_CFG['tau'],
+                   PPO_CFG['value_reg'], device=kdev)
+    e.load_replays(make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed'])))
+    theta0 = torch.from_numpy(g[key + '_theta0']).float().to(kdev)
+    valid, grad, adapted = e.ppo_meta_gradient(theta0, PPO_CFG['ppo_epochs'], PPO_CFG['ppo_clip_ratio'], anil=anil)
+    ref_ad = torch.from_numpy(g[key + '_adapted'])
+    assert rel(adapted, ref_ad) < 1e-5
+    d, dref = adapted.cpu().double() - torch.from_numpy(g[key + '_theta0']), ref_ad - torch.from_numpy(g[key + '_theta0'])
+    assert float((d - dref).norm()) <= 2e-4 * float(dref.norm()) + 2e-7 * float(ref_ad.norm())
+    if anil:        # the body did not move
+        body = slice(2, 2 + 200 + 100 + 10000 + 100)
+        assert torch.equal(adapted[:, body].cpu(), theta0[body].cpu().expand(tasks, -1))
+    assert float(valid.abs().max()) < 1e-6                              # normalised advantages: the ratio-1 loss is ~0
+    assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
+
+
+@pytest.mark.parametrize('anil', [False, True])
+def test_fast_adapt_ppo_reference_call_pattern(kdev, anil):
+    """rl/maml_ppo.py:103-129 / rl/anil_ppo.py:106-130 with the product's modules: policy.clone(), fast_adapt_ppo on a
+    stub task returning the fixture's replays, mean loss, backward() -> master .grad == the reference's."""
+    from exploring_meta_b200.core_functions import rl as xrl
+    from exploring_meta_b200.core_functions.maml import MAML
+    from exploring_meta_b200.core_functions.policies import DiagNormalPolicy, DiagNormalPolicyANIL, LinearValue
+    g = np.load(GOLD_PPO)
+    key = 'anil' if anil else 'maml'
+    tasks = int(g['tasks'])
+    policy = (DiagNormalPolicyANIL(2, 2, 100) if anil else DiagNormalPolicy(2, 2, activation='tanh')).to(kdev)
+    policy.load_flat_parameters(torch.from_numpy(g[key + '_theta0']).float().to(kdev))
+    maml = MAML(policy, lr=PPO_CFG['inner_lr'])
+    baseline = LinearValue(2, PPO_CFG['value_reg'])
+    params = dict(PPO_CFG, adapt_steps=1, adapt_batch_size=int(g['episodes']))
+    data = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']))
+
+    class StubTask:
+        def __init__(self, sup, qry):
+            self.queue = [sup, qry]
+
+        def run(self, learner, episodes=None, render=False):
+            return self.queue.pop(0)
+
+    total = 0.0
+    for t, (sup, qry) in enumerate(data):
+        learner = maml.clone()
+        loss, _rew, _suc = xrl.fast_adapt_ppo(StubTask(sup, qry), learner, baseline, params, anil=anil)
+        assert rel(learner.module.flat_parameters(), torch.from_numpy(g[key + '_adapted'][t])) < 1e-5
+        total = total + loss
+    (total / tasks).backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in policy.parameters()])
+    assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
