@@ -17,78 +17,6 @@ namespace xm {
 
 constexpr int HEAD_THREADS = 256;
 
-// Feature accessor: X[i][d] over feat[rows][hw][c].  mode 0: d = c*hw + s (NCHW flatten);
-// mode 1: d = c, X = mean over s.
-struct Feat {
-  const float* f;    // base of this task's rows
-  int hw, c, mode, row0, row_step;
-  __device__ __forceinline__ float at(int i, int d) const {
-    const long long r = (long long)(row0 + i * row_step) * hw;
-    if (mode == 0) {
-      const int ch = d / hw, s = d - ch * hw;
-      return __ldg(f + (r + s) * c + ch);
-    }
-    float acc = 0.f;
-    for (int s = 0; s < hw; ++s) acc += __ldg(f + (r + s) * c + d);
-    return acc / (float)hw;
-  }
-};
-
-// Scatter a gradient w.r.t. X[i][d] back to the feature layout (+= when accumulate).
-struct FeatGrad {
-  float* f;
-  int hw, c, mode, row0, row_step;
-  __device__ __forceinline__ void put(int i, int d, float v, bool accumulate) const {
-    const long long r = (long long)(row0 + i * row_step) * hw;
-    if (mode == 0) {
-      const int ch = d / hw, s = d - ch * hw;
-      float* q = f + (r + s) * c + ch;
-      *q = accumulate ? *q + v : v;
-    } else {
-      const float u = v / (float)hw;
-      for (int s = 0; s < hw; ++s) {
-        float* q = f + (r + s) * c + d;
-        *q = accumulate ? *q + u : u;
-      }
-    }
-  }
-};
-
-// out[i][w] = bias[w] + sum_d X(i,d)*W[w][d] (+ sum_d X2(i,d)*W2[w][d]); one warp per (i, w).
-__device__ void logits_pass(const Feat& X, const float* W, const float* bias, const Feat* X2, const float* W2,
-                            int n, int ways, int D, float* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int pr = warp; pr < n * ways; pr += nwarps) {
-    const int i = pr / ways, w = pr - i * ways;
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      acc = fmaf(X.at(i, d), W[(long long)w * D + d], acc);
-      if (X2) acc = fmaf(X2->at(i, d), W2[(long long)w * D + d], acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) out[pr] = acc + (bias ? bias[w] : 0.f);
-  }
-}
-
-// Row-wise softmax statistics.  prob <- softmax(logits); returns per-row loss and correctness through arrays.
-__device__ void softmax_rows(const float* logits, const int64_t* labels, int lab0, int lab_step, int n, int ways,
-                             float* prob, float* row_loss, int* row_ok) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float* z = logits + i * ways;
-    float mx = z[0];
-    int arg = 0;
-    for (int w = 1; w < ways; ++w)
-      if (z[w] > mx) { mx = z[w]; arg = w; }
-    float se = 0.f;
-    for (int w = 0; w < ways; ++w) se += expf(z[w] - mx);
-    const float lse = mx + logf(se);
-    const int y = (int)labels[lab0 + (long long)i * lab_step];
-    for (int w = 0; w < ways; ++w) prob[i * ways + w] = expf(z[w] - lse);
-    if (row_loss) row_loss[i] = lse - z[y];
-    if (row_ok) row_ok[i] = (arg == y) ? 1 : 0;
-  }
-}
-
 struct HeadK {
   int n, ways, c, hw, mode, dual, D;
   const float* feat; const float* feat_dot;
@@ -304,160 +232,224 @@ struct AnilK {
   const float* w; const float* b;
   float* loss; int* correct; float* g_feat;
   float* g_w; float* g_b; long long g_stride;
-  float* scratch; long long scratch_per_task;
 };
 
-__host__ __device__ inline long long anil_scratch_floats(int steps, int ways, int D, int S) {
-  const long long ph = (long long)ways * D + ways;
-  return (steps + 1) * ph          // fast weights W_0..W_T, b_0..b_T
-         + ph                      // Wb, bb (outer cotangent of the head)
-         + 2LL * steps * S * ways  // prob and dL/dlogits of every inner step
-         + 4LL * S * ways + 2LL * S;   // work arrays
-}
-
-__global__ void __launch_bounds__(HEAD_THREADS) anil_head_kernel(const AnilK k) {
-  const int task = blockIdx.x, tid = threadIdx.x;
-  const int ways = k.ways, D = k.D, S = k.S, T = k.steps;
-  const long long ph = (long long)ways * D + ways;
-  float* base = k.scratch + (long long)task * k.scratch_per_task;
-  float* Wt = base;                          // [(T+1)][ph]: W then b
-  float* Wb = Wt + (T + 1) * ph;             // [ph]
-  float* ps = Wb + ph;                       // [T][S][ways]
-  float* gls = ps + (long long)T * S * ways; // [T][S][ways]
-  float* wk0 = gls + (long long)T * S * ways;   // logits / cot   [S][ways]
-  float* wk1 = wk0 + S * ways;               // prob              [S][ways]
-  float* wk2 = wk1 + S * ways;               // glq / dl          [S][ways]
-  float* wk3 = wk2 + S * ways;               // spare             [S][ways]
-  float* row_loss = wk3 + S * ways;          // [S]
-  int* row_ok = reinterpret_cast<int*>(row_loss + S);
+// anil_head_kernel: ONE THREAD-BLOCK CLUSTER PER TASK (G <= 8 CTAs), everything resident in shared memory.  CTA r owns
+// a slice of the feature index range (native NHWC order) and keeps only that slice of the support / query rows, of
+// every fast-weight version W_0..W_T, of the outer cotangent Wb and of the support-feature gradient; the [S][ways]
+// logit-type reductions over the full feature range go through distributed shared memory (partials summed in rank
+// order by every CTA), the softmax-sized work is replicated.  Phases: T inner steps (fused SGD update of the slice),
+// query loss / accuracy / gradient, the second-order reverse sweep (softmax Hessian term included), one write of the
+// gradients.  Round 1 ran one 256-thread CTA per task out of global scratch: 1.27 ms per 32-task call (10.5 % of the
+// config-3 step).
+__global__ void __launch_bounds__(HEAD_THREADS) anil_head_kernel(const AnilK k, const int G) {
+  extern __shared__ float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int task = blockIdx.x / G, part = blockIdx.x - task * G, tid = threadIdx.x;
+  const int ways = k.ways, D = k.D, S = k.S, T = k.steps, sw = S * ways;
+  const int e_lo = (int)((long long)D * part / G), e_hi = (int)((long long)D * (part + 1) / G), span = e_hi - e_lo;
+  const int ld = ((D + G - 1) / G + 1) | 1;
+  // ---- shared-memory carve-up (identical in every CTA of the cluster: DSMEM offsets must agree) ----------------
+  float* partl = sm;                                   // [S][ways] partial logits of this slice (read by the peers)
+  float* wk0 = partl + sw;                             // [S][ways] logits / cotangent
+  float* wk1 = wk0 + sw;                               // [S][ways] query probabilities
+  float* wk2 = wk1 + sw;                               // [S][ways] glq / dl
+  float* ps = wk2 + sw;                                // [T][S][ways] softmax of every inner step
+  float* gls = ps + (size_t)T * sw;                    // [T][S][ways] dL/dlogits of every inner step
+  float* bt = gls + (size_t)T * sw;                    // [T+1][ways] biases of every version (replicated)
+  float* bb = bt + (T + 1) * ways;                     // [ways] outer cotangent of the bias
+  float* row_loss = bb + ways;                         // [S]
+  int* row_ok = reinterpret_cast<int*>(row_loss + S);  // [S]
+  float* Xs = row_loss + 2 * S;                        // [S][ld] support rows, this slice
+  float* Xq = Xs + (size_t)S * ld;                     // [S][ld] query rows
+  float* GFs = Xq + (size_t)S * ld;                    // [S][ld] gradient w.r.t. the support rows
+  float* Wt = GFs + (size_t)S * ld;                    // [T+1][ways][ld] fast weights W_0 .. W_T
+  float* Wb = Wt + (size_t)(T + 1) * ways * ld;        // [ways][ld] outer cotangent of the weights
 
   const long long fbase = (long long)task * k.rows * k.hw * k.c;
-  const Feat Fs{k.feat + fbase, k.hw, k.c, k.mode, 0, 2};
-  const Feat Fq{k.feat + fbase, k.hw, k.c, k.mode, 1, 2};
-  const FeatGrad Gs{k.g_feat + fbase, k.hw, k.c, k.mode, 0, 2};
-  const FeatGrad Gq{k.g_feat + fbase, k.hw, k.c, k.mode, 1, 2};
+  const float* F = k.feat + fbase;
   const int64_t* lab = k.labels + (long long)task * k.rows;
+  auto perm = [&](int e) { return k.mode == 0 ? (e % k.c) * k.hw + e / k.c : e; };   // native -> PyTorch feature index
+  auto label = [&](int row) { const int y = (int)lab[row]; return y < 0 ? 0 : (y >= ways ? ways - 1 : y); };
 
-  for (int i = tid; i < ways * D; i += blockDim.x) Wt[i] = k.w[i];
-  for (int i = tid; i < ways; i += blockDim.x) Wt[ways * D + i] = k.b[i];
+  // ---- stage: rows 2i = support, 2i+1 = query (prepare_batch's split), weights gathered into native order ---------
+  for (int idx = tid; idx < 2 * S * span; idx += HEAD_THREADS) {
+    const int r = idx / span, j = idx - r * span, e = e_lo + j;
+    float x;
+    if (k.mode == 0) {
+      x = __ldg(F + (long long)r * D + e);
+    } else {
+      x = 0.f;
+      for (int s = 0; s < k.hw; ++s) x += __ldg(F + ((long long)r * k.hw + s) * k.c + e);
+      x /= (float)k.hw;
+    }
+    ((r & 1) ? Xq : Xs)[(r >> 1) * ld + j] = x;
+  }
+  for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+    const int w = idx / span, j = idx - w * span;
+    Wt[w * ld + j] = __ldg(k.w + (long long)w * D + perm(e_lo + j));
+  }
+  for (int idx = tid; idx < S * span; idx += HEAD_THREADS) GFs[(idx / span) * ld + idx % span] = 0.f;
+  for (int w = tid; w < ways; w += HEAD_THREADS) bt[w] = __ldg(k.b + w);
   __syncthreads();
 
-  // ---- inner loop on the support rows ---------------------------------------------------------------
+  // full[i][w] = bias[w] + sum over the whole feature range of X[i][.] * W[w][.]: slice partials through DSMEM
+  auto logits_all = [&](const float* X, const float* W, const float* bias, float* out) {
+    for (int o = tid; o < sw; o += HEAD_THREADS) {
+      const int i = o / ways, w = o - i * ways;
+      const float* xr = X + i * ld;
+      const float* wr = W + w * ld;
+      float acc = 0.f;
+      for (int j = 0; j < span; ++j) acc = fmaf(xr[j], wr[j], acc);
+      partl[o] = acc;
+    }
+    cluster.sync();
+    for (int o = tid; o < sw; o += HEAD_THREADS) {
+      float acc = 0.f;
+      for (int r = 0; r < G; ++r) acc += cluster.map_shared_rank(partl, r)[o];       // rank order: same bits everywhere
+      out[o] = acc + bias[o % ways];
+    }
+    cluster.sync();                                    // every peer has read this CTA's partials
+  };
+  // prob <- softmax(logits) per row; optional per-row loss / correctness against labels of rows lab0 + 2 i
+  auto softmax_all = [&](const float* logits, int lab0, float* prob, bool want_loss) {
+    for (int i = tid; i < S; i += HEAD_THREADS) {
+      const float* z = logits + i * ways;
+      float mx = z[0];
+      int arg = 0;
+      for (int w = 1; w < ways; ++w)
+        if (z[w] > mx) { mx = z[w]; arg = w; }
+      float se = 0.f;
+      for (int w = 0; w < ways; ++w) se += expf(z[w] - mx);
+      const float lse = mx + logf(se);
+      for (int w = 0; w < ways; ++w) prob[i * ways + w] = expf(z[w] - lse);
+      if (want_loss) {
+        const int y = label(lab0 + 2 * i);
+        row_loss[i] = lse - z[y];
+        row_ok[i] = (arg == y) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  };
+
+  // ---- inner loop on the support rows (core_functions/vision.py:9-13 with features != None) -------------------------
   for (int t = 0; t < T; ++t) {
-    const float* W = Wt + t * ph;
-    const float* B = W + ways * D;
-    float* Wn = Wt + (t + 1) * ph;
-    float* P = ps + (long long)t * S * ways;
-    float* G = gls + (long long)t * S * ways;
-    logits_pass(Fs, W, B, nullptr, nullptr, S, ways, D, wk0);
-    __syncthreads();
-    softmax_rows(wk0, lab, 0, 2, S, ways, P, nullptr, nullptr);
-    __syncthreads();
-    for (int idx = tid; idx < S * ways; idx += blockDim.x) {
+    const float* W = Wt + (size_t)t * ways * ld;
+    float* Wn = Wt + (size_t)(t + 1) * ways * ld;
+    float* P = ps + (size_t)t * sw;
+    float* Gt = gls + (size_t)t * sw;
+    logits_all(Xs, W, bt + t * ways, wk0);
+    softmax_all(wk0, 0, P, false);
+    for (int idx = tid; idx < sw; idx += HEAD_THREADS) {
       const int i = idx / ways, w = idx - i * ways;
-      const int y = (int)lab[2 * i];
-      G[idx] = (P[idx] - (w == y ? 1.f : 0.f)) / (float)S;
+      Gt[idx] = (P[idx] - (w == label(2 * i) ? 1.f : 0.f)) / (float)S;
     }
     __syncthreads();
-    for (int idx = tid; idx < ways * D; idx += blockDim.x) {
-      const int w = idx / D, d = idx - w * D;
+    for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+      const int w = idx / span, j = idx - w * span;
       float acc = 0.f;
-      for (int i = 0; i < S; ++i) acc = fmaf(G[i * ways + w], Fs.at(i, d), acc);
-      Wn[idx] = W[idx] + (-k.lr * acc);
+      for (int i = 0; i < S; ++i) acc = fmaf(Gt[i * ways + w], Xs[i * ld + j], acc);
+      Wn[w * ld + j] = W[w * ld + j] + (-k.lr * acc);
     }
-    for (int w = tid; w < ways; w += blockDim.x) {
+    for (int w = tid; w < ways; w += HEAD_THREADS) {
       float acc = 0.f;
-      for (int i = 0; i < S; ++i) acc += G[i * ways + w];
-      Wn[ways * D + w] = B[w] + (-k.lr * acc);
+      for (int i = 0; i < S; ++i) acc += Gt[i * ways + w];
+      bt[(t + 1) * ways + w] = bt[t * ways + w] + (-k.lr * acc);
     }
     __syncthreads();
   }
 
-  // ---- query loss / accuracy at the adapted head ----------------------------------------------------
-  const float* WT = Wt + T * ph;
-  const float* BT = WT + ways * D;
-  logits_pass(Fq, WT, BT, nullptr, nullptr, S, ways, D, wk0);
-  __syncthreads();
-  softmax_rows(wk0, lab, 1, 2, S, ways, wk1, row_loss, row_ok);
-  __syncthreads();
-  if (tid == 0) {
+  // ---- query loss / accuracy at the adapted head (vision.py:15-17) ------------------------------------------------------
+  const float* WT = Wt + (size_t)T * ways * ld;
+  logits_all(Xq, WT, bt + T * ways, wk0);
+  softmax_all(wk0, 1, wk1, true);
+  if (part == 0 && tid == 0) {
     float s = 0.f;
     int ok = 0;
     for (int i = 0; i < S; ++i) { s += row_loss[i]; ok += row_ok[i]; }
     k.loss[task] = s / (float)S;
     k.correct[task] = ok;
   }
-  for (int idx = tid; idx < S * ways; idx += blockDim.x) {
+  for (int idx = tid; idx < sw; idx += HEAD_THREADS) {
     const int i = idx / ways, w = idx - i * ways;
-    const int y = (int)lab[2 * i + 1];
-    wk2[idx] = (wk1[idx] - (w == y ? 1.f : 0.f)) / (float)S;
+    wk2[idx] = (wk1[idx] - (w == label(2 * i + 1) ? 1.f : 0.f)) / (float)S;
   }
   __syncthreads();
-  // Wb = glq^T Fq, bb = sum glq ; gFq = glq W_T ; gFs = 0
-  for (int idx = tid; idx < ways * D; idx += blockDim.x) {
-    const int w = idx / D, d = idx - w * D;
+  // Wb = glq^T Xq, bb = sum glq, gXq = glq W_T
+  for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+    const int w = idx / span, j = idx - w * span;
     float acc = 0.f;
-    for (int i = 0; i < S; ++i) acc = fmaf(wk2[i * ways + w], Fq.at(i, d), acc);
-    Wb[idx] = acc;
+    for (int i = 0; i < S; ++i) acc = fmaf(wk2[i * ways + w], Xq[i * ld + j], acc);
+    Wb[w * ld + j] = acc;
   }
-  for (int w = tid; w < ways; w += blockDim.x) {
+  for (int w = tid; w < ways; w += HEAD_THREADS) {
     float acc = 0.f;
     for (int i = 0; i < S; ++i) acc += wk2[i * ways + w];
-    Wb[ways * D + w] = acc;
+    bb[w] = acc;
   }
-  for (int idx = tid; idx < S * D; idx += blockDim.x) {
-    const int i = idx / D, d = idx - i * D;
+  float* GF = k.g_feat + fbase;
+  auto put_row = [&](int row, int j, float v) {         // gradient w.r.t. feature e_lo + j of row `row`
+    const int e = e_lo + j;
+    if (k.mode == 0) {
+      GF[(long long)row * D + e] = v;
+    } else {
+      const float u = v / (float)k.hw;
+      for (int s = 0; s < k.hw; ++s) GF[((long long)row * k.hw + s) * k.c + e] = u;
+    }
+  };
+  for (int idx = tid; idx < S * span; idx += HEAD_THREADS) {
+    const int i = idx / span, j = idx - i * span;
     float acc = 0.f;
-    for (int w = 0; w < ways; ++w) acc = fmaf(wk2[i * ways + w], WT[(long long)w * D + d], acc);
-    Gq.put(i, d, acc, false);
-    Gs.put(i, d, 0.f, false);
+    for (int w = 0; w < ways; ++w) acc = fmaf(wk2[i * ways + w], WT[w * ld + j], acc);
+    put_row(2 * i + 1, j, acc);
   }
   __syncthreads();
 
-  // ---- second-order reverse sweep through the inner steps --------------------------------------------
+  // ---- second-order reverse sweep through the inner steps ------------------------------------------------------------------
   if (!k.first_order) {
     for (int t = T - 1; t >= 0; --t) {
-      const float* W = Wt + t * ph;
-      const float* P = ps + (long long)t * S * ways;
-      const float* G = gls + (long long)t * S * ways;
-      // cot[i][w] = Fs(i,:) . uW[w,:] + ub[w],  uW = -lr*Wb, ub = -lr*bb
-      logits_pass(Fs, Wb, Wb + ways * D, nullptr, nullptr, S, ways, D, wk0);
-      __syncthreads();
-      for (int i = tid; i < S; i += blockDim.x) {
+      const float* W = Wt + (size_t)t * ways * ld;
+      const float* P = ps + (size_t)t * sw;
+      const float* Gt = gls + (size_t)t * sw;
+      logits_all(Xs, Wb, bb, wk0);                     // cot[i][w] = Xs(i,:) . Wb[w,:] + bb[w]
+      for (int i = tid; i < S; i += HEAD_THREADS) {
         float pc = 0.f;
         for (int w = 0; w < ways; ++w) pc += P[i * ways + w] * (-k.lr * wk0[i * ways + w]);
         for (int w = 0; w < ways; ++w)
           wk2[i * ways + w] = P[i * ways + w] * (-k.lr * wk0[i * ways + w] - pc) / (float)S;     // dl
       }
       __syncthreads();
-      // gFs += gl_t uW + dl W_t       (uses Wb before its update)
-      for (int idx = tid; idx < S * D; idx += blockDim.x) {
-        const int i = idx / D, d = idx - i * D;
+      for (int idx = tid; idx < S * span; idx += HEAD_THREADS) {       // gXs += gl_t uW + dl W_t  (Wb before its update)
+        const int i = idx / span, j = idx - i * span;
         float acc = 0.f;
         for (int w = 0; w < ways; ++w) {
-          acc = fmaf(G[i * ways + w], -k.lr * Wb[(long long)w * D + d], acc);
-          acc = fmaf(wk2[i * ways + w], W[(long long)w * D + d], acc);
+          acc = fmaf(Gt[i * ways + w], -k.lr * Wb[w * ld + j], acc);
+          acc = fmaf(wk2[i * ways + w], W[w * ld + j], acc);
         }
-        Gs.put(i, d, acc, true);
+        GFs[i * ld + j] += acc;
       }
       __syncthreads();
-      // Wb += dl^T Fs ; bb += sum dl
-      for (int idx = tid; idx < ways * D; idx += blockDim.x) {
-        const int w = idx / D, d = idx - w * D;
+      for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {    // Wb += dl^T Xs ; bb += sum dl
+        const int w = idx / span, j = idx - w * span;
         float acc = 0.f;
-        for (int i = 0; i < S; ++i) acc = fmaf(wk2[i * ways + w], Fs.at(i, d), acc);
-        Wb[idx] += acc;
+        for (int i = 0; i < S; ++i) acc = fmaf(wk2[i * ways + w], Xs[i * ld + j], acc);
+        Wb[w * ld + j] += acc;
       }
-      for (int w = tid; w < ways; w += blockDim.x) {
+      for (int w = tid; w < ways; w += HEAD_THREADS) {
         float acc = 0.f;
         for (int i = 0; i < S; ++i) acc += wk2[i * ways + w];
-        Wb[ways * D + w] += acc;
+        bb[w] += acc;
       }
       __syncthreads();
     }
   }
-  for (int idx = tid; idx < ways * D; idx += blockDim.x) k.g_w[(long long)task * k.g_stride + idx] = Wb[idx];
-  for (int w = tid; w < ways; w += blockDim.x) k.g_b[(long long)task * k.g_stride + w] = Wb[ways * D + w];
+  for (int idx = tid; idx < S * span; idx += HEAD_THREADS) put_row(2 * (idx / span), idx % span, GFs[(idx / span) * ld + idx % span]);
+  for (int idx = tid; idx < ways * span; idx += HEAD_THREADS) {
+    const int w = idx / span, j = idx - w * span;
+    k.g_w[(long long)task * k.g_stride + (long long)w * D + perm(e_lo + j)] = Wb[w * ld + j];
+  }
+  if (part == 0)
+    for (int w = tid; w < ways; w += HEAD_THREADS) k.g_b[(long long)task * k.g_stride + w] = bb[w];
 }
 
 }  // namespace xm
@@ -514,8 +506,7 @@ extern "C" int xm_head(const XmHeadArgs* a, void* stream_) {
 
 extern "C" int64_t xm_anil_head_scratch_bytes(const XmAnilHeadArgs* a) {
   if (!a || a->tasks <= 0 || a->rows <= 0 || a->ways <= 0 || a->steps < 0) return -1;
-  const int D = a->mode == 0 ? a->c * a->hw : a->c;
-  return (int64_t)a->tasks * anil_scratch_floats(a->steps, a->ways, D, a->rows / 2) * 4;
+  return 0;          // the kernel keeps every intermediate in shared memory; `scratch` may be NULL
 }
 
 extern "C" int xm_anil_head(const XmAnilHeadArgs* a, void* stream_) {
@@ -524,7 +515,7 @@ extern "C" int xm_anil_head(const XmAnilHeadArgs* a, void* stream_) {
   XM_REQUIRE(a->tasks > 0 && a->rows > 0 && a->rows % 2 == 0 && a->ways > 0 && a->c > 0 && a->hw > 0 && a->steps >= 0,
              "xm_anil_head: bad sizes");
   XM_REQUIRE(a->mode == 0 || a->mode == 1, "xm_anil_head: bad mode");
-  XM_REQUIRE(a->feat && a->labels && a->w && a->b && a->loss && a->correct && a->g_feat && a->g_w && a->g_b && a->scratch,
+  XM_REQUIRE(a->feat && a->labels && a->w && a->b && a->loss && a->correct && a->g_feat && a->g_w && a->g_b,
              "xm_anil_head: null pointer argument");
   AnilK k{};
   k.rows = a->rows; k.ways = a->ways; k.c = a->c; k.hw = a->hw; k.mode = a->mode; k.steps = a->steps;
@@ -534,9 +525,25 @@ extern "C" int xm_anil_head(const XmAnilHeadArgs* a, void* stream_) {
   k.feat = a->feat; k.labels = a->labels; k.w = a->w; k.b = a->b;
   k.loss = a->loss; k.correct = a->correct; k.g_feat = a->g_feat;
   k.g_w = a->g_w; k.g_b = a->g_b; k.g_stride = a->g_task_stride;
-  k.scratch = a->scratch;
-  k.scratch_per_task = anil_scratch_floats(k.steps, k.ways, k.D, k.S);
-  XM_REQUIRE(a->scratch_bytes >= (int64_t)a->tasks * k.scratch_per_task * 4, "xm_anil_head: scratch too small");
-  anil_head_kernel<<<a->tasks, HEAD_THREADS, 0, stream>>>(k);
+  int G = k.D / 32;
+  if (G > 8) G = 8;
+  if (G < 1) G = 1;
+  const int ld = ((k.D + G - 1) / G + 1) | 1, sw = k.S * k.ways;
+  const size_t smem = ((size_t)4 * sw + 2 * (size_t)k.steps * sw + (size_t)(k.steps + 2) * k.ways + 2 * k.S +
+                       3 * (size_t)k.S * ld + (size_t)(k.steps + 2) * k.ways * ld) * 4;
+  XM_REQUIRE(smem <= 200 * 1024, "xm_anil_head: rows * (ways + D/8) * steps too large for shared memory");
+  XM_CUDA(cudaFuncSetAttribute(anil_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a->tasks * G));
+  cfg.blockDim = dim3(HEAD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XM_CUDA(cudaLaunchKernelEx(&cfg, anil_head_kernel, k, G));
+
   return launched("xm_anil_head");
 }

@@ -220,7 +220,8 @@ int xm_head(const XmHeadArgs* a, void* stream);
  * on the support feature rows (even rows), query loss / correct count on the odd rows, and the outer
  * gradient w.r.t. the head initialisation (g_w, g_b: per task) and w.r.t. ALL feature rows (g_feat).
  * feat is the body output for all rows of the task: [t][rows][hw][c], flattened like xm_head mode 0/1.
- * scratch >= xm_anil_head_scratch_bytes(). */
+ * One thread-block cluster per task, every intermediate in (distributed) shared memory: `scratch` is unused (may be NULL;
+ * xm_anil_head_scratch_bytes returns 0 and is kept for callers of the earlier ABI). */
 typedef struct XmAnilHeadArgs {
   int32_t tasks, rows, ways, c, hw, mode, steps, first_order;
   float lr;
