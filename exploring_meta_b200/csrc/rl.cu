@@ -228,13 +228,19 @@ __device__ __forceinline__ float act_d1(float h, int act) { return act == XM_ACT
 // d/d eps of act'(z) expressed through h and hdot: tanh: -2 h hdot; relu: 0
 __device__ __forceinline__ float act_d1_dot(float h, float hdot, int act) { return act == XM_ACT_TANH ? -2.f * h * hdot : 0.f; }
 
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float comp(const float4& v, int r) { return r == 0 ? v.x : (r == 1 ? v.y : (r == 2 ? v.z : v.w)); }
+// row stride of W2 in shared memory: a multiple of 4 floats (128-bit loads) whose quarter is odd, so that the eight
+// lanes of a load phase, which read rows i, i+1, ..., hit eight different 16-byte bank groups
+__host__ __device__ inline int rl_ldw(int h1) { int l = (h1 + 3) & ~3; if (((l >> 2) & 1) == 0) l += 4; return l; }
+
 // DF: tangent forward (theta_dot given); DB: tangent backward too (Hessian-vector product)
 template <bool DF, bool DB>
 __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int task = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int n = k.n, IN = k.in, OUT = k.out, H1 = k.h1, H2 = k.h2, act = k.act;
-  const int ldw = H1 | 1;                             // odd row stride of W2: conflict-free when lanes walk rows
+  const int ldw = rl_ldw(H1);
   // ---- shared-memory carve-up -------------------------------------------------------------------------------------
   float* p = sm;
   auto take = [&](int count) { float* q = p; p += (count + 3) & ~3; return q; };
@@ -323,22 +329,26 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int q = 0; q < 4; ++q) { acc[a][q] = 0.f; accd[a][q] = 0.f; }
-      for (int j = 0; j < H1; ++j) {
-        float av[4], dv[4], wv[4], wdv[4];
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < H1; j += 4) {                // 128-bit shared loads: 8 (16 with tangents) per 64 (192) FMAs
+        float4 av[4], dv[4], wv[4], wdv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { av[a] = A1[(ty * 4 + a) * H1 + j]; if (DF) dv[a] = D1[(ty * 4 + a) * H1 + j]; }
+        for (int a = 0; a < 4; ++a) { av[a] = lds4(A1 + (ty * 4 + a) * H1 + j); if (DF) dv[a] = lds4(D1 + (ty * 4 + a) * H1 + j); }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = tx + 32 * q;
-          wv[q] = i < H2 ? W2[i * ldw + j] : 0.f;
-          if (DF) wdv[q] = i < H2 ? W2d[i * ldw + j] : 0.f;
+          wv[q] = i < H2 ? lds4(W2 + i * ldw + j) : zero4;
+          if (DF) wdv[q] = i < H2 ? lds4(W2d + i * ldw + j) : zero4;
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            acc[a][q] = fmaf(wv[q], av[a], acc[a][q]);
-            if (DF) accd[a][q] = fmaf(wdv[q], av[a], fmaf(wv[q], dv[a], accd[a][q]));
+            acc[a][q] = fmaf(wv[q].x, av[a].x, fmaf(wv[q].y, av[a].y, fmaf(wv[q].z, av[a].z, fmaf(wv[q].w, av[a].w, acc[a][q]))));
+            if (DF) {
+              accd[a][q] = fmaf(wdv[q].x, av[a].x, fmaf(wdv[q].y, av[a].y, fmaf(wdv[q].z, av[a].z, fmaf(wdv[q].w, av[a].w, accd[a][q]))));
+              accd[a][q] = fmaf(wv[q].x, dv[a].x, fmaf(wv[q].y, dv[a].y, fmaf(wv[q].z, dv[a].z, fmaf(wv[q].w, dv[a].w, accd[a][q]))));
+            }
           }
       }
 #pragma unroll
@@ -468,71 +478,86 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
       if (tid < OUT)
         for (int s = 0; s < RL_TS; ++s) accb3 += DB ? GMUD[s * OUT + tid] : GMU[s * OUT + tid];
       __syncthreads();
-      // ---- gz1 = (W2^T gz2) * act'(h1) (+ tangent): thread = 4 samples x 4 units; written over A2 / D2 ----------------
+      // ---- gz1 = (W2^T gz2) * act'(h1) (+ tangent): thread = 4 samples x 4 CONSECUTIVE inputs j0 .. j0+3 (one 128-bit load
+      // of a W2 row per unit; lanes beyond H1 / 4 idle); written over A2 / D2 ------------------------------------------------
       {
+        const int j0 = 4 * tx;
+        const bool jact = j0 < H1;
         float acc[4][4], accd[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { acc[a][q] = 0.f; accd[a][q] = 0.f; }
-        for (int i = 0; i < H2; ++i) {
-          float gv[4], gdv[4], wv[4], wdv[4];
+          for (int c = 0; c < 4; ++c) { acc[a][c] = 0.f; accd[a][c] = 0.f; }
+        if (jact)
+          for (int i = 0; i < H2; i += 4) {
+            float4 gv[4], gdv[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) { gv[a] = G2[(ty * 4 + a) * H2 + i]; if (DB) gdv[a] = G2d[(ty * 4 + a) * H2 + i]; }
+            for (int a = 0; a < 4; ++a) { gv[a] = lds4(G2 + (ty * 4 + a) * H2 + i); if (DB) gdv[a] = lds4(G2d + (ty * 4 + a) * H2 + i); }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = tx + 32 * q;
-            wv[q] = j < H1 ? W2[i * ldw + j] : 0.f;
-            if (DB) wdv[q] = j < H1 ? W2d[i * ldw + j] : 0.f;
-          }
+            for (int r = 0; r < 4; ++r) {
+              const float4 w = lds4(W2 + (i + r) * ldw + j0);
+              float4 wd;
+              if (DB) wd = lds4(W2d + (i + r) * ldw + j0);
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              acc[a][q] = fmaf(wv[q], gv[a], acc[a][q]);
-              if (DB) accd[a][q] = fmaf(wdv[q], gv[a], fmaf(wv[q], gdv[a], accd[a][q]));
+              for (int a = 0; a < 4; ++a) {
+                const float gz = comp(gv[a], r);
+                acc[a][0] = fmaf(w.x, gz, acc[a][0]); acc[a][1] = fmaf(w.y, gz, acc[a][1]);
+                acc[a][2] = fmaf(w.z, gz, acc[a][2]); acc[a][3] = fmaf(w.w, gz, acc[a][3]);
+                if (DB) {
+                  const float gzd = comp(gdv[a], r);
+                  accd[a][0] = fmaf(wd.x, gz, fmaf(w.x, gzd, accd[a][0])); accd[a][1] = fmaf(wd.y, gz, fmaf(w.y, gzd, accd[a][1]));
+                  accd[a][2] = fmaf(wd.z, gz, fmaf(w.z, gzd, accd[a][2])); accd[a][3] = fmaf(wd.w, gz, fmaf(w.w, gzd, accd[a][3]));
+                }
+              }
             }
-        }
+          }
         __syncthreads();                               // every thread is done reading A2 / D2 of this tile
-        // G1 lives in the A2 buffer, G1d in D2 (H1 == H2 strides are handled by indexing with H1 inside capacity:
-        // both buffers hold RL_TS * max(H1, H2) floats, see the host-side size computation)
+        // G1 lives in the A2 buffer, G1d in D2 (both hold RL_TS * max(H1, H2) floats, see the host-side size computation)
+        if (jact)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 4; ++a) {
+            const int s = ty * 4 + a;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = tx + 32 * q, s = ty * 4 + a;
-            if (j < H1) {
+            for (int c = 0; c < 4; ++c) {
+              const int j = j0 + c;
               const float h = A1[s * H1 + j], d1 = act_d1(h, act);
-              A2[s * H1 + j] = acc[a][q] * d1;
-              if (DB) D2[s * H1 + j] = accd[a][q] * d1 + acc[a][q] * act_d1_dot(h, D1[s * H1 + j], act);
+              A2[s * H1 + j] = acc[a][c] * d1;
+              if (DB) D2[s * H1 + j] = accd[a][c] * d1 + acc[a][c] * act_d1_dot(h, D1[s * H1 + j], act);
             }
           }
       }
       __syncthreads();
-      // ---- weight gradient of layer 2: thread owns units i = ty + 8 q, inputs j = tx + 32 r --------------------------------
-      for (int s = 0; s < RL_TS; ++s) {
-        float hv[4], hdv[4];
+      // ---- weight gradient of layer 2: thread owns unit blocks 4 (ty + 8 q) .. +3 and inputs 4 tx .. 4 tx + 3 -------------
+      {
+        const int j0 = 4 * tx;
+        if (j0 < H1)
+          for (int s = 0; s < RL_TS; ++s) {
+            const float4 hv = lds4(A1 + s * H1 + j0);
+            float4 hdv;
+            if (DB) hdv = lds4(D1 + s * H1 + j0);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int j = tx + 32 * r;
-          hv[r] = j < H1 ? A1[s * H1 + j] : 0.f;
-          if (DB) hdv[r] = j < H1 ? D1[s * H1 + j] : 0.f;
-        }
+            for (int q = 0; q < 4; ++q) {
+              const int i0 = 4 * (ty + 8 * q);
+              if (i0 < H2) {
+                const float4 g4 = lds4(G2 + s * H2 + i0);
+                float4 gd4;
+                if (DB) gd4 = lds4(G2d + s * H2 + i0);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int i = ty + 8 * q;
-          if (i < H2) {
-            const float gz = G2[s * H2 + i];
-            if (DB) {
-              const float gzd = G2d[s * H2 + i];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) accW2[q][r] = fmaf(gzd, hv[r], fmaf(gz, hdv[r], accW2[q][r]));
-            } else {
-#pragma unroll
-              for (int r = 0; r < 4; ++r) accW2[q][r] = fmaf(gz, hv[r], accW2[q][r]);
+                for (int ii = 0; ii < 4; ++ii) {
+                  const float gz = comp(g4, ii);
+                  float* acc = accW2[4 * q + ii];
+                  if (DB) {
+                    const float gzd = comp(gd4, ii);
+                    acc[0] = fmaf(gzd, hv.x, fmaf(gz, hdv.x, acc[0])); acc[1] = fmaf(gzd, hv.y, fmaf(gz, hdv.y, acc[1]));
+                    acc[2] = fmaf(gzd, hv.z, fmaf(gz, hdv.z, acc[2])); acc[3] = fmaf(gzd, hv.w, fmaf(gz, hdv.w, acc[3]));
+                  } else {
+                    acc[0] = fmaf(gz, hv.x, acc[0]); acc[1] = fmaf(gz, hv.y, acc[1]);
+                    acc[2] = fmaf(gz, hv.z, acc[2]); acc[3] = fmaf(gz, hv.w, acc[3]);
+                  }
+                }
+              }
             }
           }
-        }
       }
       // ---- layer-1 gradients: thread = hidden unit ----------------------------------------------------------------------------
       if (tid < H1) {
@@ -581,13 +606,10 @@ __global__ void __launch_bounds__(RL_THREADS) rl_sweep_kernel(const SweepK k) {
     if (tid < OUT) out[ob3 + tid] = accb3;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int i = ty + 8 * q;
-      if (i < H2) {
+      const int i = 4 * (ty + 8 * (q >> 2)) + (q & 3);
+      if (i < H2 && 4 * tx < H1) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int j = tx + 32 * r;
-          if (j < H1) out[oW2 + i * H1 + j] = accW2[q][r];
-        }
+        for (int r = 0; r < 4; ++r) out[oW2 + i * H1 + 4 * tx + r] = accW2[q][r];
       }
     }
   }
@@ -643,6 +665,7 @@ static int sweep_check(const XmRlSweepArgs* a) {
   XM_REQUIRE(a->tasks > 0 && a->n > 0 && a->in_dim >= 1 && a->in_dim <= RL_MAXIO && a->out_dim >= 1 &&
              a->out_dim <= RL_MAXIO && a->h1 >= 1 && a->h1 <= RL_MAXH && a->h2 >= 1 && a->h2 <= RL_MAXH,
              "xm_rl_sweep: bad sizes (dims <= 8, hidden <= 128)");
+  XM_REQUIRE(a->h1 % 4 == 0 && a->h2 % 4 == 0, "xm_rl_sweep: hidden widths must be multiples of 4 (128-bit shared loads)");
   XM_REQUIRE(a->activation == XM_ACT_RELU || a->activation == XM_ACT_TANH, "xm_rl_sweep: bad activation");
   XM_REQUIRE(a->loss >= XM_RL_A2C && a->loss <= XM_RL_FISHER && a->what >= XM_RL_FORWARD && a->what <= XM_RL_HVP,
              "xm_rl_sweep: bad loss / what");
@@ -687,7 +710,7 @@ extern "C" int xm_rl_sweep(const XmRlSweepArgs* a, void* stream_) {
   k.partial_sc = reinterpret_cast<double*>(reinterpret_cast<char*>(a->partial) +
                                            (((int64_t)a->tasks * k.G * k.P + 1) / 2) * 2 * 4);
   auto pad = [](int c) { return (c + 3) & ~3; };
-  const int IN = a->in_dim, OUT = a->out_dim, H1 = a->h1, H2 = a->h2, ldw = H1 | 1, HM = H1 > H2 ? H1 : H2;
+  const int IN = a->in_dim, OUT = a->out_dim, H1 = a->h1, H2 = a->h2, ldw = rl_ldw(H1), HM = H1 > H2 ? H1 : H2;
   const int wset = pad(OUT) + pad(H1 * IN) + pad(H1) + pad(H2 * ldw) + pad(H2) + pad(OUT * H2) + pad(OUT);
   int fl = wset * (DF ? 2 : 1);
   fl += pad(RL_TS * H1) + pad(RL_TS * HM);                          // A1, A2 (A2 also holds gz1: max width)

@@ -180,12 +180,12 @@ class _EngineBase:
         a.scratch = _p(self.img_scratch)
         return a
 
-    def _emit_gram(self, prog, n, img, gram):
+    def _emit_gram(self, prog, n, img, gram, lane=0):
         a = XmImgArgs()
         a.g, a.eps = self.geom(0, n), BN_EPS
         a.row0, a.row_step, a.rows_per_task = img
         a.x, a.gram = _p(self.x), _p(gram)
-        prog.emit('xm_img_gram', a)
+        prog.emit('xm_img_gram', a, lane=lane)
 
     def _emit_img_fwd(self, prog, n, img, gram, theta, tstride, st, Pout, MI, call_stats):
         a = self._img_args(n, img, gram, theta, tstride)
@@ -415,13 +415,16 @@ class MamlEngine(_EngineBase):
         sup, qry = (0, 2, self.rows), (1, 2, self.rows)
         if self.img:                                   # Gram matrices of the support / query images, once
             self._emit_gram(prog, S, sup, self.gram_sup)
-            self._emit_gram(prog, S, qry, self.gram_qry)
+            # the query rows' Gram matrix is first read by the query pass (phase 2): parallel branch, joined with the
+            # first inner step's weight gradients
+            self._emit_gram(prog, S, qry, self.gram_qry, lane=1 if T > 0 else 0)
         # ---- phase 1: T inner steps on the support rows (core_functions/vision.py:9-13) ----------
         for t in range(T):
             k = t if self.mode == 'second' else 0
             th, ts = self._theta(t)
             nxt = self.theta_steps[t]
-            prog.join()                                # theta_t complete (weight gradients of step t-1 run on the side lane)
+            if t > 0:
+                prog.join()                            # theta_t complete (weight gradients of step t-1 run on the side lane)
             for l in range(L):
                 self._emit_block_fwd(prog, l, S, self.Pa[k][l - 1] if l else None, sup, th, ts,
                                      self.Z[k][l], self.Pa[k][l], self.MI[k][l], self.call_stats[t, l])
