@@ -20,15 +20,78 @@
 // core's own accumulation truncates), and each CTA writes one partial block per task split;
 // wgrad_reduce_kernel (wgrad.cu) reduces the splits in double and applies the fused SGD / outer-recursion
 // epilogue.
+//
+// FP16-split variant (template parameter F16, xm_set_precision(2)) -- where the split pays: this kernel is bound by
+// shared-memory traffic (producer stores 88 KB + MMA operand reads 336 KB per tile against 128 B/clk; drain is light).
+//   * operands: position rows of 64 B (32 channels of fp16) in the SWIZZLE_64B MN-major layout, decoded on hardware
+//     with scripts/probe_umma_f16.cu: element (mn, k) at start + (mn/32)*LBO + (k/8)*SBO + (k%8)*64 +
+//     (((mn%32)/8) ^ ((row >> 1) & 3))*16 + (mn%8)*2 with row = ABSOLUTE shared address >> 6 -- so, exactly as in the
+//     TF32 layout, LBO = one position row makes the M groups the tile shifted by kw rows, LBO = Wp rows makes the N
+//     groups the halo shifted by kernel rows, and a start address shifted by whole rows addresses the same data;
+//   * x * s = hi + lo with hi = fp16(x * s), lo = fp16(x * s - hi): a power-of-two scale s per staged tile and operand
+//     (from the tile's absolute maximum: producer warps post their maxima and arrive on an mbarrier BEFORE waiting
+//     for the stage) brings the maximum to [2^14, 2^15), so lo is a normal fp16 for every element within 2^17 of the
+//     maximum and the absolute error of the rest is 2^-39 of it -- no separate correction accumulator is needed;
+//   * K = 16 position rows per MMA: 8 K steps x 3 terms = 24 MMAs per (tile, pair) unit instead of 48; half the staged
+//     bytes; every unit is drained on its own (its scale is its own) with the power-of-two un-scaling in the drain.
+// Measured (scripts/diag_wgrad.py, 42x42, 32 tasks): accuracy against fp64 4.9e-7 (3xTF32: 8.8e-7); 193 us against 197 us.
+// With the global loads compiled out the FP16 kernel takes 83 us and the TF32 one 145 us: the split halves the
+// tensor / shared-memory side, but what bounds the kernel is the producers' global -> register -> convert -> shared
+// path (address arithmetic, 256-bit loads, conversions in 7 warps).  A per-thread cp.async ring three units deep
+// (more bytes in flight, raw fp32 rows in shared memory) was 25 % SLOWER -- the extra shared-memory round trip costs
+// more than the latency it hides.  The next step is bulk (TMA) row copies issued by one thread.
+#include <cuda_fp16.h>
 #include "tc.cuh"
 
 namespace xm {
+
+extern int g_precise;                        // conv.cu: 2 selects the FP16-split variant
 
 constexpr int WT_DRAINERS = 128;             // warps 0-3: warp kw < 3 drains TMEM lane quarter kw (warp 3 idles)
 constexpr int WT_PRODUCERS = 224;            // warps 4-10
 constexpr int WT_THREADS = WT_DRAINERS + WT_PRODUCERS + 32;   // + the MMA-issuing warp 11 (12 warps: 168 registers)
 constexpr int WT_TMEM_COLS = 256;            // 2 sets x 3 accumulators x 32 columns (192) -> next power of two
 constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 96, 1, 1);   // A and B MN-major, N = 3 kernel rows x 32 cout
+// kind::f16: fp16 inputs, fp32 accumulate, A and B MN-major
+constexpr uint32_t WT_IDESC_F16 = (1u << 4) | (1u << 15) | (1u << 16) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// power-of-two scale 2^k that brings a maximum magnitude m into [2^14, 2^15); k = 0 for m = 0
+__device__ __forceinline__ int wt_scale_exp(float m) {
+  if (!(m > 0.f)) return 0;
+  const int k = 14 - (int)((__float_as_uint(m) >> 23) & 0xffu) + 127;
+  return max(-100, min(100, k));
+}
+__device__ __forceinline__ float wt_exp2i(int k) { return __uint_as_float((uint32_t)(127 + k) << 23); }
+__device__ __forceinline__ float wt_absmax(const float4& v) {
+  return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+// 8 floats -> 8 fp16 hi + 8 fp16 lo (16 bytes each).  hi is rounded to 11 significant bits in fp32 first (two integer
+// ops, like split_tf32_fast), so the packing conversion is exact for normal fp16 values and lo = x*s - hi is exact.
+__device__ __forceinline__ void wt_split_f16(const float4& a, const float4& b, float sc, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float h0 = __uint_as_float((__float_as_uint(x[2 * i]) + 0x1000u) & 0xFFFFE000u);
+    const float h1 = __uint_as_float((__float_as_uint(x[2 * i + 1]) + 0x1000u) & 0xFFFFE000u);
+    const __half2 hh = __floats2half2_rn(h0, h1);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 struct WgradTcK {
   int tasks, n, H, W, Hp, Wp, Q;
@@ -42,12 +105,20 @@ struct WgradTcK {
   int x_cs, x_co, g_cs, g_co;         // floats per position of x / g and the first channel of this launch's 32-channel block
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK p) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xset = p.xbuf, gset = p.gbuf;
+  constexpr int ROWB = F16 ? 64 : 128;                 // bytes of one staged position row
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // FP16 variant: per-unit maxima of the x tile / g halo (float bits), the unit's combined scale exponent, and the
+  // "every producer warp has posted its maxima" barriers
+  uint32_t* smaxx = reinterpret_cast<uint32_t*>(bars + 10);      // [4]
+  uint32_t* smaxg = smaxx + 4;                                   // [4]
+  int* uexp = reinterpret_cast<int*>(smaxg + 4);                 // [4]
+  const uint32_t bar_max = smem_u32(bars + 16);                  // [2]
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
                  bar_tfree = smem_u32(bars + 6);
 
@@ -57,7 +128,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       mbar_init(bar_sfree + 8 * s, 1);
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tfree + 8 * s, 96);
+      if (F16) mbar_init(bar_max + 8 * s, WT_PRODUCERS / 32);
     }
+    if (F16)
+      for (int i = 0; i < 4; ++i) { smaxx[i] = 0u; smaxg[i] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 11) {
@@ -66,9 +140,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // rows past Rx (read only by the unused 4th lane group) must hold finite values
-  for (int i = tid; i < (xset - p.Rx * 128) / 16; i += WT_THREADS) {
+  for (int i = tid; i < (xset - p.Rx * ROWB) / 16; i += WT_THREADS) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t o = (size_t)p.Rx * 128 + (size_t)i * 16;
+    const size_t o = (size_t)p.Rx * ROWB + (size_t)i * 16;
     *reinterpret_cast<float4*>(smem + p.off_x0 + o) = zero;
     *reinterpret_cast<float4*>(smem + p.off_x0 + xset + o) = zero;
     *reinterpret_cast<float4*>(smem + p.off_x1 + o) = zero;
@@ -112,6 +186,27 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         }
       };
       int cur_task = g_lo / p.tiles_per_task;
+      if (F16) {
+        // every (tile, pair) unit has its own power-of-two scale: drained on its own, un-scaled while adding
+        for (int u = 0; u < nunits; ++u) {
+          const int set = u & 1, it = u / p.npairs;
+          const int t_task = (g_lo + it) / p.tiles_per_task;
+          if (t_task != cur_task) { flush(cur_task); cur_task = t_task; }
+          mbar_wait(bar_tfull + 8 * set, (u >> 1) & 1);
+          tc_fence_after();
+          const float unscale = wt_exp2i(-uexp[u & 3]);
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(set * 96);
+          float v[32];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            tmem_ld32(taddr + (uint32_t)(kh * 32), v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) macc[kh][c] = fmaf(v[c], unscale, macc[kh][c]);
+          }
+          tc_fence_before();
+          mbar_arrive(bar_tfree + 8 * set);
+        }
+      } else
       for (int it = 0; it < ntiles; ++it) {
         const int set = it & 1;
         const int t_task = (g_lo + it) / p.tiles_per_task;
@@ -165,9 +260,58 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     };
     auto store = [&](int u, const Regs& r) {
       const int s = u & 1;
+      if (F16) {
+        float mx = 0.f, mg = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mx = fmaxf(mx, wt_absmax(r.x[k]));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mg = fmaxf(mg, wt_absmax(r.g[k]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+        }
+        if (lane == 0) {
+          atomicMax(&smaxx[u & 3], __float_as_uint(mx));
+          atomicMax(&smaxg[u & 3], __float_as_uint(mg));
+          mbar_arrive(bar_max + 8 * s);
+        }
+      }
       if (u >= 2) mbar_wait(bar_sfree + 8 * s, ((u - 2) >> 1) & 1);     // MMAs of unit u-2 have read stage s
       unsigned char* xhi = smem + (s ? p.off_x1 : p.off_x0);
       unsigned char* ghi = smem + (s ? p.off_g1 : p.off_g0);
+      if (F16) {
+        mbar_wait(bar_max + 8 * s, (u >> 1) & 1);
+        const int kx = wt_scale_exp(__uint_as_float(smaxx[u & 3])), kg = wt_scale_exp(__uint_as_float(smaxg[u & 3]));
+        // slots of unit u + 2 were last read for unit u - 2: every producer has since passed two of these waits
+        if (ptid == 0) { uexp[u & 3] = kx + kg; smaxx[(u + 2) & 3] = 0u; smaxg[(u + 2) & 3] = 0u; }
+        const float sx = wt_exp2i(kx), sg = wt_exp2i(kg);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int j = jrow + PR * k;
+          if (j < p.Rx) {
+            const size_t o = (size_t)j * 64 + (size_t)((c8 ^ ((j >> 1) & 3)) * 16);   // 16 B chunk swizzled with the row pair
+            uint4 h, l;
+            wt_split_f16(r.x[2 * k], r.x[2 * k + 1], sx, h, l);
+            *reinterpret_cast<uint4*>(xhi + o) = h;
+            *reinterpret_cast<uint4*>(xhi + xset + o) = l;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = jrow + PR * k;
+          if (i < p.Rg) {
+            const size_t o = (size_t)i * 64 + (size_t)((c8 ^ ((i >> 1) & 3)) * 16);
+            uint4 h, l;
+            wt_split_f16(r.g[2 * k], r.g[2 * k + 1], sg, h, l);
+            *reinterpret_cast<uint4*>(ghi + o) = h;
+            *reinterpret_cast<uint4*>(ghi + gset + o) = l;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+        return;
+      }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int j = jrow + PR * k;
@@ -213,10 +357,36 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     // ======================================= MMA issuer =================================================
     for (int u = 0; u < nunits; ++u) {
       const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
-      const int set = it & 1;
+      const int set = F16 ? (u & 1) : (it & 1);
       mbar_wait(bar_full + 8 * s, (u >> 1) & 1);
-      if (pair == 0 && it >= 2) mbar_wait(bar_tfree + 8 * set, ((it - 2) >> 1) & 1);
+      if (F16) {
+        if (u >= 2) mbar_wait(bar_tfree + 8 * set, ((u - 2) >> 1) & 1);
+      } else if (pair == 0 && it >= 2) {
+        mbar_wait(bar_tfree + 8 * set, ((it - 2) >> 1) & 1);
+      }
       tc_fence_after();
+      if (F16) {
+        if (elect_one_sync()) {
+          // rows of 64 B, SWIZZLE_64B (layout type 4), SBO = 8 rows; A: LBO = one row, B: LBO = Wp rows; K = 16 rows
+          const uint32_t x_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_x1 : p.off_x0)), 64u);
+          const uint32_t x_lo0 = x_hi0 + (uint32_t)(xset >> 4);
+          const uint32_t g_hi0 = umma_desc_lo(smem_u32(smem + (s ? p.off_g1 : p.off_g0)), (uint32_t)p.Wp * 64u);
+          const uint32_t g_lo0 = g_hi0 + (uint32_t)(gset >> 4);
+          constexpr uint32_t dhi = umma_desc_hi(512u, 4u);
+          const uint32_t d = tmem_base + (uint32_t)(set * 96);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 64u;                   // 16 position rows of 64 B per K step
+            umma_f16_lh(d, x_lo0 + ko, dhi, g_hi0 + ko, dhi, WT_IDESC_F16, ks == 0 ? 0u : 1u);
+            umma_f16_lh(d, x_hi0 + ko, dhi, g_lo0 + ko, dhi, WT_IDESC_F16, 1u);
+            umma_f16_lh(d, x_hi0 + ko, dhi, g_hi0 + ko, dhi, WT_IDESC_F16, 1u);
+          }
+          umma_commit(bar_sfree + 8 * s);
+          umma_commit(bar_tfull + 8 * set);
+        }
+        __syncwarp();
+        continue;
+      }
       if (elect_one_sync()) {
         // descriptor low words (start address | LBO); per MMA only the start field moves.  A = x tile with
         // LBO = one position row (lane group kw = tile shifted by kw rows), B = g halo with LBO = Wp position rows
@@ -250,7 +420,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   }
 }
 
-static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
+static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem, bool f16 = (g_precise == 2)) {
   if (g.cin != g.cout || (g.cout != 32 && g.cout != 64) || (g.stride != 1 && g.stride != 2)) return false;
   p.n = g.n; p.H = g.hin; p.W = g.win; p.Hp = g.hin + 1; p.Wp = g.win + 1;
   p.Q = g.n * p.Hp * p.Wp;
@@ -258,14 +428,16 @@ static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem) {
   p.tiles_per_task = (p.Q + 127) / 128;
   p.Rx = 128 + 3;                                    // x tile + the three kw shifts
   p.Rg = 128 + 2 * p.Wp;                             // g halo: kernel rows shift it by 0, Wp, 2*Wp rows
-  p.xbuf = ((p.Rx + 1 + 7) & ~7) * 128;              // + the row the unused lane group reads; whole 1 KB units
-  p.gbuf = ((p.Rg + 7) & ~7) * 128;                  // keep every buffer 1024 B aligned
+  const int rowb = f16 ? 64 : 128, ralign = f16 ? 15 : 7;
+  p.xbuf = ((p.Rx + 1 + ralign) & ~ralign) * rowb;   // + the row the unused lane group reads; whole 1 KB units
+  p.gbuf = ((p.Rg + ralign) & ~ralign) * rowb;       // keep every buffer 1024 B aligned
   p.off_x0 = 0;
   p.off_g0 = p.off_x0 + 2 * p.xbuf;
   p.off_x1 = p.off_g0 + 2 * p.gbuf;
   p.off_g1 = p.off_x1 + 2 * p.xbuf;
   p.off_bar = p.off_g1 + 2 * p.gbuf;
-  smem = (size_t)p.off_bar + 8 * 8 + 16;
+  const int bar_bytes = 8 * 8 + 16 + 12 * 4 + 16 + 2 * 8;
+  smem = (size_t)p.off_bar + bar_bytes;
   // partial slots per task = the most CTAs of the persistent grid that can touch one task
   const long long total = (long long)g.tasks * p.tiles_per_task;
   p.ctas = (int)(total < num_sms() ? total : num_sms());
@@ -301,8 +473,9 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   p.npairs = a->x2 ? 2 : 1;
   p.x[0] = a->x1; p.g[0] = a->g1; p.x[1] = a->x2; p.g[1] = a->g2;
   p.partial = a->partial;
+  auto kern = g_precise == 2 ? wgrad_tc_kernel<true> : wgrad_tc_kernel<false>;
   {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
   }
   // block (cb, ib) of a wide layer: gW[32 cb .. +31][32 ib .. +31] from g's channel block cb and x's channel block ib,
@@ -323,7 +496,7 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
     for (int ib = 0; ib < blocks; ++ib) {
       p.g_co = 32 * cb; p.x_co = 32 * ib;
       p.partial = a->partial + (long long)(cb * blocks + ib) * g.tasks * p.splits * 9 * 32 * 32;
-      wgrad_tc_kernel<<<p.ctas, WT_THREADS, smem, stream>>>(p);
+      kern<<<p.ctas, WT_THREADS, smem, stream>>>(p);
       if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
     }
   *ctas_out = p.ctas;

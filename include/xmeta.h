@@ -371,9 +371,11 @@ int xm_bn_ema(float* running_mean, float* running_var, const float* call_stats, 
               int64_t outer_stride, int32_t n_inner, int64_t inner_stride, int32_t channels,
               float momentum, void* stream);
 
-/* Contraction precision of xm_conv / xm_wgrad: 1 (default) = error-compensated 3xTF32 (fp32-level
- * accuracy, what the parity contract is stated in); 0 = single-pass TF32 (faster, ~1e-3 relative error
- * per contraction).  Process-wide; set before building / capturing a launch program. */
+/* Contraction precision of xm_conv / xm_wgrad: 1 (default) = error-compensated 3xTF32 (fp32-level accuracy, what the
+ * parity contract is stated in); 0 = single-pass TF32 (faster, ~1e-3 relative error per contraction); 2 = the same
+ * 3-term expansion on fp16 hi / lo pairs with per-tile power-of-two scaling on the tcgen05 kernels (kind::f16: equal
+ * or better accuracy than 1, measured NOT faster -- DESIGN section 8 -- kept for A/B comparison; XM_PRECISION=2 in the
+ * environment selects it at load time).  Process-wide; set before building / capturing a launch program. */
 int xm_set_precision(int precise);
 /* Kernel selection for A/B comparison.  1 (default): 32-channel stride-1 contractions run on the tcgen05 / TMEM
  * kernels and the image layer (cin <= 4, stride 1) on the exact-fp32 CUDA-core kernel; 2: the image-layer forward

@@ -7,6 +7,9 @@ from exploring_meta_b200 import _lib
 from exploring_meta_b200._lib import XmBlockGeom, XmWgradArgs, XmConvArgs
 
 lib = _lib.load()
+if len(sys.argv) > 1:
+    lib.xm_set_precision(int(sys.argv[1]))
+    print('precision', sys.argv[1])
 st = torch.cuda.current_stream().cuda_stream
 
 
@@ -30,6 +33,13 @@ def run(tasks, n, hw, realistic):
     a.partial, a.partial_bytes = part.data_ptr(), nbytes
     _lib.check(lib.xm_wgrad(ctypes.byref(a), st), 'xm_wgrad')
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(10):
+        lib.xm_wgrad(ctypes.byref(a), st)
+    ev1.record()
+    torch.cuda.synchronize()
+    us = ev0.elapsed_time(ev1) * 100.0
     xd = x.double().permute(0, 1, 4, 2, 3)
     gd = gz.double().permute(0, 1, 4, 2, 3)
     ref = torch.stack([torch.nn.grad.conv2d_weight(xd[t], (32, 32, 3, 3), gd[t], padding=1) for t in range(tasks)])
@@ -38,8 +48,8 @@ def run(tasks, n, hw, realistic):
     e = ((got - ref).norm() / ref.norm()).item()
     e32 = ((ref32.double() - ref).norm() / ref.norm()).item()
     es = ((got.sum(0) - ref.sum(0)).norm() / ref.sum(0).norm()).item()
-    print('wgrad tasks %3d n %2d %2dx%2d %s: rel-L2 ours %.2e  torch-fp32 %.2e   task-sum ours %.2e' % (
-        tasks, n, hw, hw, 'bn-like' if realistic else 'randn ', e, e32, es))
+    print('wgrad tasks %3d n %2d %2dx%2d %s: rel-L2 ours %.2e  torch-fp32 %.2e   task-sum ours %.2e   %7.1f us (incl. reduce) %5.1f TF' % (
+        tasks, n, hw, hw, 'bn-like' if realistic else 'randn ', e, e32, es, us, 2.0 * tasks * n * hw * hw * 9 * 32 * 32 / us / 1e6))
 
 
 for realistic in (False, True):
