@@ -39,8 +39,12 @@
 // tensor / shared-memory side, but what bounds the kernel is the producers' global -> register -> convert -> shared
 // path (address arithmetic, 256-bit loads, conversions in 7 warps).  A per-thread cp.async ring three units deep
 // (more bytes in flight, raw fp32 rows in shared memory) was 25 % SLOWER -- the extra shared-memory round trip costs
-// more than the latency it hides.  The next step is bulk (TMA) row copies issued by one thread.
+// more than the latency it hides.  Bulk (TMA) row copies issued by one loader warp into the same ring (XM_WT_TMA=1:
+// cp.async.bulk per image row, padding positions zeroed by the loader, producers convert shared -> shared) are correct
+// and slower still (231 us): per unit the producers then wait 2300 cycles for the copies although they are issued
+// three units ahead -- the memory system delivers ~1.9 TB/s to these 148 persistent streams whatever the request depth.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "tc.cuh"
 
 namespace xm {
@@ -64,6 +68,14 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint
       "setp.ne.b32 p, %6, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 1-D bulk (TMA) copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // power-of-two scale 2^k that brings a maximum magnitude m into [2^14, 2^15); k = 0 for m = 0
 __device__ __forceinline__ int wt_scale_exp(float m) {
@@ -99,6 +111,7 @@ struct WgradTcK {
   int tiles_per_task, splits, npairs, ctas;
   int Rx, Rg, xbuf, gbuf;             // staged x / g rows per tile, bytes of one x / g buffer (hi or lo)
   int off_x0, off_x1, off_g0, off_g1, off_bar;   // shared-memory byte offsets
+  int off_raw, raw_stage, raw_stages;            // FP16 variant: ring of raw fp32 tiles landed by bulk (TMA) copies; 0 stages = off
   const float* x[2];
   const float* g[2];
   float* partial;                     // [task][split][9*32][32]
@@ -119,6 +132,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
   uint32_t* smaxg = smaxx + 4;                                   // [4]
   int* uexp = reinterpret_cast<int*>(smaxg + 4);                 // [4]
   const uint32_t bar_max = smem_u32(bars + 16);                  // [2]
+  const uint32_t bar_rfull = smem_u32(bars + 18), bar_rfree = smem_u32(bars + 21);   // [3] each: raw ring (TMA) full / free
+  const int NR = p.raw_stages;
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4),
                  bar_tfree = smem_u32(bars + 6);
 
@@ -130,8 +145,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       mbar_init(bar_tfree + 8 * s, 96);
       if (F16) mbar_init(bar_max + 8 * s, WT_PRODUCERS / 32);
     }
-    if (F16)
+    if (F16) {
       for (int i = 0; i < 4; ++i) { smaxx[i] = 0u; smaxg[i] = 0u; }
+      for (int i = 0; i < 3; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rfree + 8 * i, WT_PRODUCERS / 32); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 11) {
@@ -188,11 +205,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       int cur_task = g_lo / p.tiles_per_task;
       if (F16) {
         // every (tile, pair) unit has its own power-of-two scale: drained on its own, un-scaled while adding
+#ifdef XM_TC_TIMING
+        long long tw = 0, td = 0, t0;
+#endif
         for (int u = 0; u < nunits; ++u) {
           const int set = u & 1, it = u / p.npairs;
           const int t_task = (g_lo + it) / p.tiles_per_task;
           if (t_task != cur_task) { flush(cur_task); cur_task = t_task; }
+#ifdef XM_TC_TIMING
+          t0 = clock64();
+#endif
           mbar_wait(bar_tfull + 8 * set, (u >> 1) & 1);
+#ifdef XM_TC_TIMING
+          tw += clock64() - t0; t0 = clock64();
+#endif
           tc_fence_after();
           const float unscale = wt_exp2i(-uexp[u & 3]);
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(set * 96);
@@ -205,7 +231,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           }
           tc_fence_before();
           mbar_arrive(bar_tfree + 8 * set);
+#ifdef XM_TC_TIMING
+          td += clock64() - t0;
+#endif
         }
+#ifdef XM_TC_TIMING
+        if (blockIdx.x == 0 && tid == 0) printf("drain: per unit wait-tfull %lld drain %lld (units %d)\n", tw / nunits, td / nunits, nunits);
+#endif
       } else
       for (int it = 0; it < ntiles; ++it) {
         const int set = it & 1;
@@ -225,6 +257,63 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         mbar_arrive(bar_tfree + 8 * set);
       }
       if (ntiles > 0) flush(cur_task);
+    } else if (F16 && NR > 0) {
+      // ===================================== bulk-copy loader (warp 3) =====================================
+      // Positions differ from pixels only by the padding column of every row and the padding row of every image, so
+      // the rows a unit needs are a handful of contiguous pixel runs: one 1-D bulk copy (TMA) per image row lands them
+      // as raw fp32 position rows in a ring NR units deep; the padding positions of the slot are zeroed by this warp.
+      // The producer warps then only convert shared -> shared: no position arithmetic, no global loads in 224 threads.
+      const int Qtask = p.Q;
+      for (int u = 0; u < nunits; ++u) {
+        const int st = u % NR;
+        if (u >= NR) mbar_wait(bar_rfree + 8 * st, ((u / NR) - 1) & 1);
+        const int it = u / p.npairs, pair = u - it * p.npairs;
+        const int gtile = g_lo + it, task = gtile / p.tiles_per_task;
+        const int q0 = (gtile - task * p.tiles_per_task) * 128;
+        const float* srcs[2] = {p.x[pair] + (long long)task * p.n * p.H * p.W * 32, p.g[pair] + (long long)task * p.n * p.H * p.W * 32};
+        unsigned char* raw = smem + p.off_raw + (size_t)st * p.raw_stage;
+        const float* my_src[2] = {nullptr, nullptr};
+        uint32_t my_dst[2] = {0u, 0u}, my_bytes[2] = {0u, 0u};
+#pragma unroll
+        for (int seg = 0; seg < 2; ++seg) {
+          const int base_q = seg == 0 ? q0 - 1 : q0 - p.Wp, R = seg == 0 ? p.Rx : p.Rg;
+          unsigned char* dst0 = raw + (seg == 0 ? 0 : (size_t)p.Rx * 128);
+          for (int j = lane; j < R; j += 32)                       // zero rows at padding / out-of-range positions
+            if (pos_to_pixel(p.pm, base_q + j) < 0) {
+              float4* z = reinterpret_cast<float4*>(dst0 + (size_t)j * 128);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          const int qa = max(base_q, 0), qb = min(base_q + R, Qtask);
+          if (qa < qb) {
+            const int ra = (int)fastdiv((uint32_t)qa, p.pm.drow), rb = (int)fastdiv((uint32_t)(qb - 1), p.pm.drow);
+            const int rr = ra + lane;                                // global row index img * Hp + r
+            if (rr <= rb) {
+              const int rowq = rr * p.Wp;
+              const int img = (int)fastdiv((uint32_t)rowq, p.pm.dimg), r = rr - img * p.Hp;
+              const int c_lo = max(qa, rowq) - rowq, c_hi = min(min(qb, rowq + p.W) - rowq, p.W);
+              if (r >= 1 && c_hi > c_lo) {
+                my_src[seg] = srcs[seg] + ((long long)(img * p.H + r - 1) * p.W + c_lo) * 32;
+                my_dst[seg] = smem_u32(dst0 + (size_t)(rowq + c_lo - base_q) * 128);
+                my_bytes[seg] = (uint32_t)(c_hi - c_lo) * 128u;
+              }
+            }
+          }
+        }
+        uint32_t total = my_bytes[0] + my_bytes[1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        fence_proxy_async();                                       // generic zero stores / earlier reads before async-proxy writes
+        __syncwarp();
+        if (lane == 0) {
+          if (total) mbar_arrive_expect_tx(bar_rfull + 8 * st, total);
+          else mbar_arrive(bar_rfull + 8 * st);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int seg = 0; seg < 2; ++seg)
+          if (my_bytes[seg]) bulk_g2s(my_dst[seg], my_src[seg], my_bytes[seg], bar_rfull + 8 * st);
+      }
     }
   } else if (warp < 11) {
     // ========================================= producers =============================================
@@ -237,6 +326,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     const int ptid = tid - WT_DRAINERS;
     const int c8 = ptid & 3, jrow = ptid >> 2;
     struct Regs { float4 x[6]; float4 g[8]; };
+#ifdef XM_TC_TIMING
+    long long g_wsf = 0, g_max = 0, g_mw = 0, g_conv = 0, g_fence = 0;
+#endif
     auto issue = [&](int u, Regs& r) {
       const int it = u / p.npairs, pair = u - it * p.npairs;
       const int gtile = g_lo + it, task = gtile / p.tiles_per_task;
@@ -260,6 +352,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
     };
     auto store = [&](int u, const Regs& r) {
       const int s = u & 1;
+#ifdef XM_TC_TIMING
+      long long tp = clock64();
+#endif
       if (F16) {
         float mx = 0.f, mg = 0.f;
 #pragma unroll
@@ -277,11 +372,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           mbar_arrive(bar_max + 8 * s);
         }
       }
+#ifdef XM_TC_TIMING
+      const long long ts0 = clock64();
+      g_max += ts0 - tp;
+#endif
       if (u >= 2) mbar_wait(bar_sfree + 8 * s, ((u - 2) >> 1) & 1);     // MMAs of unit u-2 have read stage s
+#ifdef XM_TC_TIMING
+      g_wsf += clock64() - ts0; tp = clock64();
+#endif
       unsigned char* xhi = smem + (s ? p.off_x1 : p.off_x0);
       unsigned char* ghi = smem + (s ? p.off_g1 : p.off_g0);
       if (F16) {
         mbar_wait(bar_max + 8 * s, (u >> 1) & 1);
+#ifdef XM_TC_TIMING
+        g_mw += clock64() - tp; tp = clock64();
+#endif
         const int kx = wt_scale_exp(__uint_as_float(smaxx[u & 3])), kg = wt_scale_exp(__uint_as_float(smaxg[u & 3]));
         // slots of unit u + 2 were last read for unit u - 2: every producer has since passed two of these waits
         if (ptid == 0) { uexp[u & 3] = kx + kg; smaxx[(u + 2) & 3] = 0u; smaxg[(u + 2) & 3] = 0u; }
@@ -308,8 +413,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
             *reinterpret_cast<uint4*>(ghi + gset + o) = l;
           }
         }
+#ifdef XM_TC_TIMING
+        g_conv += clock64() - tp; tp = clock64();
+#endif
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
+#ifdef XM_TC_TIMING
+        g_fence += clock64() - tp;
+#endif
         return;
       }
 #pragma unroll
@@ -343,6 +454,53 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     };
+    if (F16 && NR > 0) {
+      Regs r;
+#ifdef XM_TC_TIMING
+      long long t_rf = 0, t_all = 0, t0, t1;
+#endif
+      for (int u = 0; u < nunits; ++u) {
+        const int st = u % NR;
+#ifdef XM_TC_TIMING
+        t0 = clock64();
+#endif
+        mbar_wait(bar_rfull + 8 * st, (u / NR) & 1);               // the unit's rows have landed
+#ifdef XM_TC_TIMING
+        t1 = clock64(); t_rf += t1 - t0;
+#endif
+        const unsigned char* raw = smem + p.off_raw + (size_t)st * p.raw_stage;
+        const unsigned char* rawg = raw + (size_t)p.Rx * 128;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int j = jrow + PR * k;
+          r.x[2 * k] = r.x[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < p.Rx) {
+            r.x[2 * k] = *reinterpret_cast<const float4*>(raw + (size_t)j * 128 + c8 * 32);
+            r.x[2 * k + 1] = *reinterpret_cast<const float4*>(raw + (size_t)j * 128 + c8 * 32 + 16);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = jrow + PR * k;
+          r.g[2 * k] = r.g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < p.Rg) {
+            r.g[2 * k] = *reinterpret_cast<const float4*>(rawg + (size_t)i * 128 + c8 * 32);
+            r.g[2 * k + 1] = *reinterpret_cast<const float4*>(rawg + (size_t)i * 128 + c8 * 32 + 16);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_rfree + 8 * st);            // this warp's rows are in registers
+        store(u, r);
+#ifdef XM_TC_TIMING
+        t_all += clock64() - t1;
+#endif
+      }
+#ifdef XM_TC_TIMING
+      if (blockIdx.x == 0 && (tid == WT_DRAINERS || tid == WT_DRAINERS + 200))
+        printf("producer tid %d: per unit wait-raw-full %lld | rest %lld = max+post %lld wait-sfree %lld wait-max %lld convert+store %lld fence+arrive %lld (+ raw reads)\n",
+               tid, t_rf / nunits, t_all / nunits, g_max / nunits, g_wsf / nunits, g_mw / nunits, g_conv / nunits, g_fence / nunits);
+#endif
+    } else {
     Regs ra, rb;
     if (nunits > 0) issue(0, ra);
     for (int u = 0; u < nunits; u += 2) {
@@ -353,14 +511,30 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         store(u + 1, rb);
       }
     }
+    }
   } else {
     // ======================================= MMA issuer =================================================
+#ifdef XM_TC_TIMING
+    long long m_wf = 0, m_wt = 0, m_is = 0, mt0;
+    unsigned long long ns0, ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    const long long c_begin = clock64();
+#endif
     for (int u = 0; u < nunits; ++u) {
       const int s = u & 1, it = u / p.npairs, pair = u - it * p.npairs;
       const int set = F16 ? (u & 1) : (it & 1);
+#ifdef XM_TC_TIMING
+      mt0 = clock64();
+#endif
       mbar_wait(bar_full + 8 * s, (u >> 1) & 1);
+#ifdef XM_TC_TIMING
+      m_wf += clock64() - mt0; mt0 = clock64();
+#endif
       if (F16) {
         if (u >= 2) mbar_wait(bar_tfree + 8 * set, ((u - 2) >> 1) & 1);
+#ifdef XM_TC_TIMING
+        m_wt += clock64() - mt0; mt0 = clock64();
+#endif
       } else if (pair == 0 && it >= 2) {
         mbar_wait(bar_tfree + 8 * set, ((it - 2) >> 1) & 1);
       }
@@ -385,6 +559,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           umma_commit(bar_tfull + 8 * set);
         }
         __syncwarp();
+#ifdef XM_TC_TIMING
+        m_is += clock64() - mt0;
+        if (u == nunits - 1 && blockIdx.x == 0 && lane == 0) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+          printf("mma: per unit wait-full %lld wait-tfree %lld issue %lld; %lld cycles in %llu ns = %.3f GHz, %d units\n", m_wf / nunits,
+                 m_wt / nunits, m_is / nunits, clock64() - c_begin, ns1 - ns0, (double)(clock64() - c_begin) / (double)(ns1 - ns0), nunits);
+        }
+#endif
         continue;
       }
       if (elect_one_sync()) {
@@ -436,8 +618,22 @@ static bool wgrad_tc_layout(const XmBlockGeom& g, WgradTcK& p, size_t& smem, boo
   p.off_x1 = p.off_g0 + 2 * p.gbuf;
   p.off_g1 = p.off_x1 + 2 * p.xbuf;
   p.off_bar = p.off_g1 + 2 * p.gbuf;
-  const int bar_bytes = 8 * 8 + 16 + 12 * 4 + 16 + 2 * 8;
+  const int bar_bytes = 8 * 8 + 16 + 12 * 4 + 16 + 2 * 8 + 6 * 8;
   smem = (size_t)p.off_bar + bar_bytes;
+  p.off_raw = 0; p.raw_stage = 0; p.raw_stages = 0;
+  // Bulk-copy (TMA) loader: opt-in (XM_WT_TMA=1).  Correct, but measured SLOWER than the register-prefetch producers
+  // (42x42, 32 tasks: 231 us against 193 us): the kernel is bound by how fast the memory system feeds 148 persistent
+  // CTAs (~1.9 TB/s), not by request latency or producer instructions, and the raw ring adds shared-memory traffic.
+  static const bool want_tma = getenv("XM_WT_TMA") && atoi(getenv("XM_WT_TMA")) != 0;
+  if (f16 && want_tma && g.cout == 32) {      // contiguous 128 B position rows: as many raw stages (2..3) as fit
+    const int off_raw = (p.off_bar + bar_bytes + 127) & ~127, stage = (p.Rx + p.Rg) * 128;
+    int stages = (227 * 1024 - off_raw) / stage;
+    if (stages > 3) stages = 3;
+    if (stages >= 2) {
+      p.off_raw = off_raw; p.raw_stage = stage; p.raw_stages = stages;
+      smem = (size_t)off_raw + (size_t)stages * stage;
+    }
+  }
   // partial slots per task = the most CTAs of the persistent grid that can touch one task
   const long long total = (long long)g.tasks * p.tiles_per_task;
   p.ctas = (int)(total < num_sms() ? total : num_sms());
