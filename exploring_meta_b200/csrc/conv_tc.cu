@@ -62,9 +62,11 @@ constexpr int TC_GROUPS = XM_TC_GROUPS;          // drain groups: group g drains
                                       // latency-bound (TMEM loads, shuffles, exchange) and ~1.5x the MMA time of a tile,
                                       // so two tiles are drained concurrently (16 warps: 128 registers each)
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
+constexpr int TC_STG_BYTES = 32 * 128 + 32 * 8;   // per drain WARP: its 32 accumulator rows (128 B each, chunks XOR-swizzled) + 32 output offsets
 constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows minus the two shifted-out rows
 constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
+constexpr uint32_t TC_IDESC2 = umma_idesc_tf32(128, 192, 0, 0); // N = [hi weights | lo weights]: two expansion terms per A read
 // kind::f16: fp16 inputs (a_format = b_format = 0), fp32 accumulate
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // M = 128, N = 32 (one tap)
 constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   // it + G need the TMEM set that tile it + G - 2 releases, which needs tile it's set released first), so the parity
   // wait is unambiguous -- per-set barriers are not: a group would see only every G-th phase of them.
   const uint32_t bar_tfull = smem_u32(mxbars + 2);
+  unsigned char* stg_base = reinterpret_cast<unsigned char*>(mxbars + 2 + TC_GROUPS + (TC_GROUPS & 1));   // 16-byte aligned
   const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfree = smem_u32(bars + 6);
 
   if (tid == 0) {
@@ -240,10 +243,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         reinterpret_cast<__half*>(Bhi)[idx] = h;
         reinterpret_cast<__half*>(Blo)[idx] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
       } else {
-        const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
+        // B[kh][c4][n2][4]: rows n2 < 96 = hi weights, n2 >= 96 = lo weights (one N = 192 operand slab)
+        const int idx = (((kh * 8 + (k >> 2)) * 192) + kw * 32 + n) * 4 + (k & 3);
         const float hi = __uint_as_float(f2tf32(v));
         Bhi[idx] = hi;
-        Blo[idx] = v - hi;
+        Bhi[idx + 96 * 4] = v - hi;
       }
     }
   }
@@ -268,7 +272,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         const int j = jrow + PR * u;
         const int px = j < p.R ? pos_to_pixel(p.pm, qbase + PR * u) : -1;
         v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef XM_TC_NOPROD
         if (px >= 0) ldg256(S + (long long)px * p.src_cs, v[2 * u], v[2 * u + 1]);
+#endif
       }
     };
 #ifdef XM_TC_TIMING
@@ -324,6 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       }
       unsigned char* hi = Abase + (size_t)(2 * s) * set_bytes + (size_t)(2 * c8) * plane;
       unsigned char* lo = hi + set_bytes;
+#ifndef XM_TC_NOPROD
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = jrow + PR * u;
@@ -337,6 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           *reinterpret_cast<float4*>(lo + plane + (size_t)j * 16) = l;
         }
       }
+#endif
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
 #ifdef XM_TC_TIMING
@@ -378,6 +386,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     // lane l with channel l's partial (2 doubles of state instead of 64 per-thread fp32 accumulators -- this is what
     // lets 16 warps fit the register file)
     double dsum = 0.0, dsq = 0.0;
+    // per-warp staging of the finished rows: stores and statistics read it back TRANSPOSED (8 lanes per row for the
+    // stores: 128 contiguous bytes per row and instruction; lane = channel for the column sums) -- no shuffles
+    float4* wst4 = reinterpret_cast<float4*>(stg_base + (size_t)(warp - 8) * TC_STG_BYTES);
+    const float* wst = reinterpret_cast<const float*>(wst4);
+    long long* wso = reinterpret_cast<long long*>(wst4 + 32 * 8);
 #ifdef XM_TC_TIMING
     long long t_wait = 0, t_tmem = 0, t_rest = 0, t0, t_bar = 0, t_fix = 0, t_store = 0, t_stat = 0;
 #endif
@@ -400,8 +413,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       tc_fence_after();
       const int xslot = group * 2 + ((it / TC_GROUPS) & 1);       // boundary-row exchange: two alternating slots per group
       const float unscale = F16 ? exp2i(-(a_exp[it & 3] + *b_exp)) : 1.f;
-      const long long o_pair = __shfl_xor_sync(0xffffffffu, o, 1);
-      const bool v_pair = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * (F16 ? 64 : 192));
       // ---- TMEM phase: both 16-column halves -> registers (kw shifts applied), then the set is released --------
       auto load_half = [&](int half, float (&acc)[16]) {
@@ -492,74 +503,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       __syncwarp();
       t_fix += clock64() - t0; t0 = clock64();
 #endif
-      // ---- epilogue of both halves: (accumulate), statistics, paired full-sector stores --------------------------
+      // ---- epilogue: rows -> per-warp staging -> coalesced stores (or vector reductions) and the statistics --------
+      __syncwarp();                                              // the previous tile's reads of the staging are complete
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float (&acc)[16] = acc2[half];
-        // Store with full 32-byte sectors: lanes (2i, 2i+1) swap half of their float4s so that in every store
-        // instruction the pair writes 32 contiguous bytes of ONE row (a thread's own row is 4 float4 = 64 B of
-        // this half; 16-byte pieces of 32 different rows per instruction would be partial-sector writes).
-        {
-          const bool odd = lane & 1;
-          float rx[4], ry[4];
+      for (int k = 0; k < 8; ++k) {
+        const float* a4 = &acc2[k >> 2][(k & 3) * 4];
+        wst4[lane * 8 + (k ^ (lane & 7))] = valid ? make_float4(a4[0], a4[1], a4[2], a4[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      wso[lane] = valid ? o : -1ll;
+      __syncwarp();
+#ifndef XM_TC_NOSTORE
+      {
+        const int c = lane & 7, rsub = lane >> 3;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            rx[k] = __shfl_xor_sync(0xffffffffu, odd ? acc[k] : acc[4 + k], 1);        // odd sends #0, even sends #1
-            ry[k] = __shfl_xor_sync(0xffffffffu, odd ? acc[8 + k] : acc[12 + k], 1);   // odd sends #2, even sends #3
-          }
-          // even lane: own #0, own #2, partner's #0, partner's #2;  odd lane: partner's #1, partner's #3, own #1, own #3
-          const long long o_first = odd ? o_pair : o, o_second = odd ? o : o_pair;
-          const bool v_first = odd ? v_pair : valid, v_second = odd ? valid : v_pair;
-          const int col = half * 16 + (odd ? 4 : 0);
-          // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector
-          // reductions -- no read of the old value, so no load latency in the drain
-          if (v_first) {
-            float* d = p.out + o_first + col;
-            put4(d, odd ? make_float4(rx[0], rx[1], rx[2], rx[3]) : make_float4(acc[0], acc[1], acc[2], acc[3]), p.accumulate);
-            put4(d + 8, odd ? make_float4(ry[0], ry[1], ry[2], ry[3]) : make_float4(acc[8], acc[9], acc[10], acc[11]), p.accumulate);
-          }
-          if (v_second) {
-            float* d = p.out + o_second + col;
-            put4(d, odd ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(rx[0], rx[1], rx[2], rx[3]), p.accumulate);
-            put4(d + 8, odd ? make_float4(acc[12], acc[13], acc[14], acc[15]) : make_float4(ry[0], ry[1], ry[2], ry[3]), p.accumulate);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const int r = 4 * k + rsub;
+          const float4 v = wst4[r * 8 + (c ^ (r & 7))];
+          const long long orow = wso[r];
+          // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector reductions
+          if (orow >= 0) put4(p.out + orow + c * 4, v, p.accumulate);
         }
       }
+#endif
 #ifdef XM_TC_TIMING
       t_store += clock64() - t0; t0 = clock64();
 #endif
       if (p.stat_mode) {
-        // v1 = this row's 32 outputs (0 for rows that produce none), v2 = v1^2 or v1 * aux
-        float v1[32], v2[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v1[k] = valid ? acc2[k >> 4][k & 15] : 0.f;
+        // column sums over the warp's 32 rows (rows that produce no output were staged as zeros): lane = channel
+        float s1 = 0.f, s2 = 0.f;
+        const int cch = lane >> 2, cin4 = lane & 3;
         if (p.stat_mode == XM_STAT_SUM_SQ) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) v2[k] = v1[k] * v1[k];
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j) {
+            const float z = wst[j * 32 + ((cch ^ (j & 7)) << 2) + cin4];
+            s1 += z;
+            s2 = fmaf(z, z, s2);
+          }
         } else {
-          const float4* ax = reinterpret_cast<const float4*>(p.aux + o);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 a4 = __ldg(ax + k);
-            v2[4 * k] = v1[4 * k] * a4.x; v2[4 * k + 1] = v1[4 * k + 1] * a4.y;
-            v2[4 * k + 2] = v1[4 * k + 2] * a4.z; v2[4 * k + 3] = v1[4 * k + 3] * a4.w;
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            float z[8], av[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const long long orow = wso[j0 + j];
+              av[j] = __ldg(p.aux + (orow >= 0 ? orow : 0ll) + lane);
+              z[j] = wst[(j0 + j) * 32 + ((cch ^ ((j0 + j) & 7)) << 2) + cin4];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1 += z[j]; s2 = fmaf(z[j], av[j], s2); }
           }
         }
-        // reduce-scatter over the 32 lanes: at offset `off` a lane keeps the half of its values whose channel bit
-        // `off` equals its own lane bit and receives the partner's copy of that half (31 shuffles per array)
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool up = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < off; ++i) {
-            const float s1 = __shfl_xor_sync(0xffffffffu, up ? v1[i] : v1[i + off], off);
-            const float s2 = __shfl_xor_sync(0xffffffffu, up ? v2[i] : v2[i + off], off);
-            v1[i] = (up ? v1[i + off] : v1[i]) + s1;
-            v2[i] = (up ? v2[i + off] : v2[i]) + s2;
-          }
-        }
-        dsum += (double)v1[0];
-        dsq += (double)v2[0];
+        dsum += (double)s1;
+        dsq += (double)s2;
       }
 #ifdef XM_TC_TIMING
       t_stat += clock64() - t0;
@@ -605,7 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       if (elect_one_sync()) {
         // descriptor low words (start address | LBO) of the stage; per MMA only the start field moves
         const uint32_t a_base = smem_u32(Abase + (size_t)(2 * s) * set_bytes);
-        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 96u * 16u), b_lo0 = umma_desc_lo(smem_u32(Blo), 96u * 16u);
+        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 192u * 16u);
         constexpr uint32_t dhi = umma_desc_hi(128u);
         const uint32_t d0 = tmem_base + (uint32_t)(s * 192);
         const uint32_t a_hi0 = umma_desc_lo(a_base, (uint32_t)plane);
@@ -637,13 +632,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t ao = shift + (uint32_t)ks * kstep;
-            const uint32_t bo = (uint32_t)((kh * 8 + 2 * ks) * 96);   // 16 B units, compile-time
+            const uint32_t bo = (uint32_t)((kh * 8 + 2 * ks) * 192);  // 16 B units, compile-time
 #ifdef XM_TC_NOMMA
             if (kh == 0 && ks == 0) {
 #endif
-            umma_tf32_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | ks) != 0));
-            umma_tf32_lh(d0 + 96, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC, 1u);
-            umma_tf32_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | ks) != 0));
+            // hi x [hi | lo] in ONE MMA (N = 192: columns [0, 96) hi*hi, [96, 192) hi*lo), then lo x hi onto the
+            // correction columns: 17 KB of operand reads per K step instead of 21 KB, 24 MMAs per tile instead of 36
+            umma_tf32_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC2, (uint32_t)((kh | ks) != 0));
+            umma_tf32_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, 1u);
 #ifdef XM_TC_NOMMA
             }
 #endif
@@ -681,7 +677,8 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes, bool f16) {
   const int rpad = R | 1;                 // odd row count per plane: conflict-free 16 B stores across planes
   plane_bytes = rpad * 16;
   const int nplanes = f16 ? 4 : 8, bwords = f16 ? 3 * 4 * 96 * 4 : 3 * 8 * 96 * 4;
-  return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + (size_t)TC_GROUPS * 2 * 2 * 4 * 3 * 16 * 4 + 16 * 4 + 2 * 8 + TC_GROUPS * 8;
+  return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + (size_t)TC_GROUPS * 2 * 2 * 4 * 3 * 16 * 4 + 16 * 4 + 2 * 8 +
+         (TC_GROUPS + (TC_GROUPS & 1)) * 8 + (size_t)TC_GROUPS * 4 * TC_STG_BYTES;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),

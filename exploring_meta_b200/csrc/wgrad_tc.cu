@@ -52,8 +52,9 @@ namespace xm {
 extern int g_precise;                        // conv.cu: 2 selects the FP16-split variant
 
 constexpr int WT_DRAINERS = 128;             // warps 0-3: warp kw < 3 drains TMEM lane quarter kw (warp 3 idles)
-constexpr int WT_PRODUCERS = 224;            // warps 4-10
+constexpr int WT_PRODUCERS = 224;            // warps 4-10 (default build: 7 producer warps)
 constexpr int WT_THREADS = WT_DRAINERS + WT_PRODUCERS + 32;   // + the MMA-issuing warp 11 (12 warps: 168 registers)
+constexpr int WT_NPW_TMA = 11;               // producer warps of the bulk-copy (TMA) variant: converters only, 40 registers of state
 constexpr int WT_TMEM_COLS = 256;            // 2 sets x 3 accumulators x 32 columns (192) -> next power of two
 constexpr uint32_t WT_IDESC = umma_idesc_tf32(128, 96, 1, 1);   // A and B MN-major, N = 3 kernel rows x 32 cout
 // kind::f16: fp16 inputs, fp32 accumulate, A and B MN-major
@@ -118,8 +119,9 @@ struct WgradTcK {
   int x_cs, x_co, g_cs, g_co;         // floats per position of x / g and the first channel of this launch's 32-channel block
 };
 
-template <bool F16>
-__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK p) {
+template <bool F16, int NPW>
+__global__ void __launch_bounds__(WT_DRAINERS + NPW * 32 + 32, 1) wgrad_tc_kernel(const WgradTcK p) {
+  constexpr int NPROD = NPW * 32, NTHREADS = WT_DRAINERS + NPROD + 32, MMA_WARP = 4 + NPW;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xset = p.xbuf, gset = p.gbuf;
@@ -139,25 +141,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, WT_PRODUCERS);
+      mbar_init(bar_full + 8 * s, NPROD);
       mbar_init(bar_sfree + 8 * s, 1);
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tfree + 8 * s, 96);
-      if (F16) mbar_init(bar_max + 8 * s, WT_PRODUCERS / 32);
+      if (F16) mbar_init(bar_max + 8 * s, NPW);
     }
     if (F16) {
       for (int i = 0; i < 4; ++i) { smaxx[i] = 0u; smaxg[i] = 0u; }
-      for (int i = 0; i < 3; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rfree + 8 * i, WT_PRODUCERS / 32); }
+      for (int i = 0; i < 3; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rfree + 8 * i, NPW); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 11) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(WT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // rows past Rx (read only by the unused 4th lane group) must hold finite values
-  for (int i = tid; i < (xset - p.Rx * ROWB) / 16; i += WT_THREADS) {
+  for (int i = tid; i < (xset - p.Rx * ROWB) / 16; i += NTHREADS) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t o = (size_t)p.Rx * ROWB + (size_t)i * 16;
     *reinterpret_cast<float4*>(smem + p.off_x0 + o) = zero;
@@ -315,17 +317,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           if (my_bytes[seg]) bulk_g2s(my_dst[seg], my_src[seg], my_bytes[seg], bar_rfull + 8 * st);
       }
     }
-  } else if (warp < 11) {
+  } else if (warp < MMA_WARP) {
     // ========================================= producers =============================================
     // A thread moves 8 channels (one 32 B swizzle chunk) of a row with one 256-bit load; rows of a unit:
     //   x tile : j = jrow + PR*k (k < 3, j < Rx = 131)  <-> position q0 - 1 + j
     //   g halo : i = jrow + PR*k (k < 4, i < Rg = 128 + 2*Wp)  <-> position q0 - Wp + i   (zero at padding positions)
     // Register-level software pipeline: the loads of unit u+1 are issued before unit u is converted and
     // stored (two register sets used alternately).
-    constexpr int PR = WT_PRODUCERS / 4;
+    constexpr int PR = NPROD / 4;
+    constexpr int KX = (131 + PR - 1) / PR, KG = (224 + PR - 1) / PR;   // row passes per thread: x tile (131 rows), g halo (<= 224)
     const int ptid = tid - WT_DRAINERS;
     const int c8 = ptid & 3, jrow = ptid >> 2;
-    struct Regs { float4 x[6]; float4 g[8]; };
+    struct Regs { float4 x[2 * KX]; float4 g[2 * KG]; };
 #ifdef XM_TC_TIMING
     long long g_wsf = 0, g_max = 0, g_mw = 0, g_conv = 0, g_fence = 0;
 #endif
@@ -336,14 +339,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       const float* X = p.x[pair] + (long long)task * p.n * p.H * p.W * p.x_cs + p.x_co + c8 * 8;
       const float* G = p.g[pair] + (long long)task * p.n * p.H * p.W * p.g_cs + p.g_co + c8 * 8;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < KX; ++k) {
         const int j = jrow + PR * k;
         const int px = j < p.Rx ? pos_to_pixel(p.pm, q0 - 1 + j) : -1;
         r.x[2 * k] = r.x[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (px >= 0) ldg256(X + (long long)px * p.x_cs, r.x[2 * k], r.x[2 * k + 1]);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KG; ++k) {
         const int i = jrow + PR * k;
         const int px = i < p.Rg ? pos_to_pixel(p.pm, q0 - p.Wp + i) : -1;
         r.g[2 * k] = r.g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -358,9 +361,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
       if (F16) {
         float mx = 0.f, mg = 0.f;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) mx = fmaxf(mx, wt_absmax(r.x[k]));
+        for (int k = 0; k < 2 * KX; ++k) mx = fmaxf(mx, wt_absmax(r.x[k]));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mg = fmaxf(mg, wt_absmax(r.g[k]));
+        for (int k = 0; k < 2 * KG; ++k) mg = fmaxf(mg, wt_absmax(r.g[k]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         if (ptid == 0) { uexp[u & 3] = kx + kg; smaxx[(u + 2) & 3] = 0u; smaxg[(u + 2) & 3] = 0u; }
         const float sx = wt_exp2i(kx), sg = wt_exp2i(kg);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < KX; ++k) {
           const int j = jrow + PR * k;
           if (j < p.Rx) {
             const size_t o = (size_t)j * 64 + (size_t)((c8 ^ ((j >> 1) & 3)) * 16);   // 16 B chunk swizzled with the row pair
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < KG; ++k) {
           const int i = jrow + PR * k;
           if (i < p.Rg) {
             const size_t o = (size_t)i * 64 + (size_t)((c8 ^ ((i >> 1) & 3)) * 16);
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         return;
       }
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < KX; ++k) {
         const int j = jrow + PR * k;
         if (j < p.Rx) {
           const size_t o = (size_t)j * 128 + (size_t)((c8 ^ (j & 3)) * 32);   // 32 B chunk swizzled with the row
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KG; ++k) {
         const int i = jrow + PR * k;
         if (i < p.Rg) {
           const size_t o = (size_t)i * 128 + (size_t)((c8 ^ (i & 3)) * 32);
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
         const unsigned char* raw = smem + p.off_raw + (size_t)st * p.raw_stage;
         const unsigned char* rawg = raw + (size_t)p.Rx * 128;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < KX; ++k) {
           const int j = jrow + PR * k;
           r.x[2 * k] = r.x[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (j < p.Rx) {
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < KG; ++k) {
           const int i = jrow + PR * k;
           r.g[2 * k] = r.g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (i < p.Rg) {
@@ -596,7 +599,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const WgradTcK 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WT_TMEM_COLS) : "memory");
   }
@@ -669,7 +672,9 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
   p.npairs = a->x2 ? 2 : 1;
   p.x[0] = a->x1; p.g[0] = a->g1; p.x[1] = a->x2; p.g[1] = a->g2;
   p.partial = a->partial;
-  auto kern = g_precise == 2 ? wgrad_tc_kernel<true> : wgrad_tc_kernel<false>;
+  const bool tma = p.raw_stages > 0;
+  auto kern = g_precise == 2 ? (tma ? wgrad_tc_kernel<true, WT_NPW_TMA> : wgrad_tc_kernel<true, 7>) : wgrad_tc_kernel<false, 7>;
+  const int nthreads = WT_DRAINERS + (tma ? WT_NPW_TMA : 7) * 32 + 32;
   {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { *rc_out = fail((int)e, "cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return -1; }
@@ -692,7 +697,7 @@ int wgrad_tc_try(const XmWgradArgs* a, cudaStream_t stream, int* rc_out, int* ct
     for (int ib = 0; ib < blocks; ++ib) {
       p.g_co = 32 * cb; p.x_co = 32 * ib;
       p.partial = a->partial + (long long)(cb * blocks + ib) * g.tasks * p.splits * 9 * 32 * 32;
-      kern<<<p.ctas, WT_THREADS, smem, stream>>>(p);
+      kern<<<p.ctas, nthreads, smem, stream>>>(p);
       if (int rc = launched("xm_wgrad(tcgen05)")) { *rc_out = rc; return -1; }
     }
   *ctas_out = p.ctas;

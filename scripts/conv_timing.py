@@ -22,3 +22,20 @@ for _ in range(2):
     tiles = (Q + 125) // 126
     print('--- kernel %.1f us; %d tiles per task, %.1f per SM -> %.3f us per tile' % (
         ev0.elapsed_time(ev1) * 1e3, tiles, 32 * tiles / 148.0, ev0.elapsed_time(ev1) * 1e3 / (32 * tiles / 148.0)))
+if os.environ.get('XM_TIMING_REPS'):
+    # steady-state figure: mean over back-to-back launches on two alternating input / output sets (> L2 together)
+    reps = int(os.environ['XM_TIMING_REPS'])
+    x2, out2 = torch.randn_like(x), torch.empty_like(x)
+    b = XmConvArgs(); b.g = g; b.mode = 0; b.stat_mode = 1
+    b.src1, b.w1, b.w1_task_stride, b.out, b.stats = x2.data_ptr(), w.data_ptr(), 9216, out2.data_ptr(), stats.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(4):
+        lib.xm_conv(ctypes.byref(a if i & 1 else b), st)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(reps):
+        lib.xm_conv(ctypes.byref(a if i & 1 else b), st)
+    ev1.record()
+    torch.cuda.synchronize()
+    us = ev0.elapsed_time(ev1) * 1e3 / reps
+    print('=== steady state: %.1f us per launch (memset + kernel), %.3f us per tile and SM' % (us, us / (32 * tiles / 148.0)))
