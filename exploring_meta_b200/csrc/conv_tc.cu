@@ -19,11 +19,12 @@
 // simply the same plane at LBO = (offset of tap t+1 - offset of tap t) * 16 B.
 //
 // Precision: parity is stated in fp32, so every product is evaluated as a 3-term TF32 expansion
-// (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; hi = rna_tf32(x), lo = x - hi): the producer warps split the
-// activations while staging, the MMA thread issues 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8) per K step.
-// The tensor core adds into fp32 accumulators with truncation, so long accumulation chains drift; the tile
-// therefore uses FOUR TMEM accumulators -- one per kernel row kh for the hi*hi terms (12 MMAs each) and one for
-// all small correction terms -- which the epilogue sums with round-to-nearest adds.
+// (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi; hi = rna_tf32(x), lo = x - hi): the producer warps split the activations
+// while staging.  The three kw taps are stacked in N (columns kw*32 + cout) and so are the hi / lo weights: per kernel
+// row kh and channel octet the MMA thread issues hi x [hi | lo] as ONE tcgen05.mma (kind::tf32, M = 128, N = 192,
+// K = 8) and lo x hi as a second one (N = 96) onto the correction columns -- 24 MMAs per tile.  The tensor core adds
+// into fp32 accumulators with truncation, so the small correction terms get their own 96 TMEM columns next to the
+// hi*hi ones and the drain sums the two with round-to-nearest adds.
 //
 // FP16-split variant (template parameter F16, xm_set_precision(2)): the same 3-term expansion on kind::f16 -- twice the
 // tensor rate of kind::tf32 and half the shared-memory bytes per element, the two things that bound this kernel.
@@ -40,10 +41,11 @@
 //
 // Pipeline (warp-specialised, 1 CTA per SM, 512 threads): warps 0-6 stage tiles (global -> TF32 split -> smem), one
 // elected lane of warp 7 issues the MMAs, warps 8-11 and 12-15 are two drain groups working on alternate tiles
-// (tcgen05.ld -> kw shift-add -> NHWC store + BatchNorm statistics; warp w reads TMEM lane quarter w%4).  Two
-// shared-memory stages and two TMEM accumulator sets; mbarrier full/free handshakes; tcgen05.commit signals
-// completion.  Measured (XM_TC_TIMING, scripts/gpu_tc_timing.sh): with two drain groups the producers' stores and the
-// MMAs' operand reads share the shared-memory bandwidth and bound a tile at ~2900 cycles (MMA stream alone ~2100).
+// (warp w reads TMEM lane quarter w%4: tcgen05.ld -> kw shift-add across lanes -> the warp's 32 finished rows staged in
+// 4 KB of its own shared memory -> read back transposed: 8 lanes per row for coalesced NHWC stores, lane = channel for
+// the BatchNorm column sums).  Two shared-memory stages and two TMEM accumulator sets; mbarrier full/free handshakes;
+// tcgen05.commit signals completion.  Measured (XM_TC_TIMING, scripts/gpu_tc_timing.sh, scripts/gpu_conv_elim.sh;
+// DESIGN.md section 8): every role alone needs 115-140 us of the 42x42 forward's 166 us.
 // 64-channel and stride-2 layers reuse this kernel through channel-block / full-resolution passes (conv_tc_try).
 #include <cuda_fp16.h>
 #include "tc.cuh"
@@ -382,9 +384,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     const int quarter = warp & 3;                              // TMEM lane quarter of this warp (= warp id % 4)
     const int group = (warp - 8) >> 2;
     const int row = quarter * 32 + lane;
-    // BatchNorm statistics: after each tile the warp's 32 rows are summed with a shuffle reduce-scatter, which leaves
-    // lane l with channel l's partial (2 doubles of state instead of 64 per-thread fp32 accumulators -- this is what
-    // lets 16 warps fit the register file)
+    // BatchNorm statistics: after each tile the warp's 32 staged rows are summed per channel (lane l = channel l: 2
+    // doubles of state instead of 64 per-thread fp32 accumulators -- this is what lets 16 warps fit the register file)
     double dsum = 0.0, dsq = 0.0;
     // per-warp staging of the finished rows: stores and statistics read it back TRANSPOSED (8 lanes per row for the
     // stores: 128 contiguous bytes per row and instruction; lane = channel for the column sums) -- no shuffles
@@ -432,7 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
             // boundary rows for the previous warp: lane 0 publishes its kw = 1 block
             if (lane == 0) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) xb[k] = v[k];
+              for (int k = 0; k < 4; ++k)
+                reinterpret_cast<float4*>(xb)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -442,7 +444,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           } else if (kw == 2) {
             if (lane < 2) {                                         // lanes 0 and 1 publish their kw = 2 blocks
 #pragma unroll
-              for (int k = 0; k < 16; ++k) xb[16 + lane * 16 + k] = v[k];
+              for (int k = 0; k < 4; ++k)
+                reinterpret_cast<float4*>(xb + 16 + lane * 16)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -482,20 +485,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       t_bar += clock64() - t0; t0 = clock64();
 #endif
       if (!F16 && lane >= 30) {
+        // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
+        // (16-byte loads of BOTH halves issued before the first use: one shared-memory round trip instead of 96)
+        float4 a[2][4], b[2][4];
+        const int oa = lane == 31 ? 0 : 4;                       // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
-          // (16-byte loads, all issued before the first use: one shared-memory round trip instead of 48)
           const float4* xn = reinterpret_cast<const float4*>(xch + (((xslot * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
-          float4 a[4], b[4];
-          const int oa = lane == 31 ? 0 : 4;                     // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { a[k] = xn[oa + k]; b[k] = xn[8 + k]; }
+          for (int k = 0; k < 4; ++k) { a[half][k] = xn[oa + k]; b[half][k] = xn[8 + k]; }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 z = lane == 31 ? b[k] : make_float4(0.f, 0.f, 0.f, 0.f);   // lane 31 adds kw=2 of row +2 (lane 1)
-            acc2[half][4 * k] += a[k].x + z.x; acc2[half][4 * k + 1] += a[k].y + z.y;
-            acc2[half][4 * k + 2] += a[k].z + z.z; acc2[half][4 * k + 3] += a[k].w + z.w;
+            const float4 z = lane == 31 ? b[half][k] : make_float4(0.f, 0.f, 0.f, 0.f);   // lane 31 adds kw=2 of row +2 (lane 1)
+            acc2[half][4 * k] += a[half][k].x + z.x; acc2[half][4 * k + 1] += a[half][k].y + z.y;
+            acc2[half][4 * k + 2] += a[half][k].z + z.z; acc2[half][4 * k + 3] += a[half][k].w + z.w;
           }
         }
       }
@@ -515,14 +521,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifndef XM_TC_NOSTORE
       {
         const int c = lane & 7, rsub = lane >> 3;
+        float4 v[8];
+        long long orow[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; ++k) {                            // all reads first: one shared-memory round trip
           const int r = 4 * k + rsub;
-          const float4 v = wst4[r * 8 + (c ^ (r & 7))];
-          const long long orow = wso[r];
-          // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector reductions
-          if (orow >= 0) put4(p.out + orow + c * 4, v, p.accumulate);
+          v[k] = wst4[r * 8 + (c ^ (r & 7))];
+          orow[k] = wso[r];
         }
+        // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector reductions
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (orow[k] >= 0) put4(p.out + orow[k] + c * 4, v[k], p.accumulate);
       }
 #endif
 #ifdef XM_TC_TIMING
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   } else {
     // ======================================= MMA issuer =================================================
     // per tile: for every kernel row kh and channel octet ks, ONE A tile (the halo at row offset kh*Wp) against
-    // the [8 x 96] weight slab of the three kw taps; 3 expansion terms -> 36 MMAs (M=128, N=96, K=8).
+    // the [8 x 192] slab of the three kw taps' hi and lo weights; 3 expansion terms in 2 MMAs -> 24 per tile.
 #ifdef XM_TC_TIMING
     long long t_wf = 0, t_wt = 0, t_issue = 0, t0;
     unsigned long long ns0, ns1;
