@@ -325,16 +325,20 @@ static int wgrad_img_splits(const XmBlockGeom& g) {
 // out_b[task][co] = base_b (the conv-bias gradient is analytically zero under train-mode BN).
 // ctas > 0: the partials come from a persistent grid of `ctas` CTAs over the flattened (task, tile) list
 // (wgrad_tc.cu); task t then owns slots 0 .. last(t) - first(t) of its `splits` slots.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
                                     float* out_w, float* out_b, long long out_stride,
                                     const float* base_w, const float* base_b, long long base_stride,
                                     float scale, int ctas = 0, int tiles_per_task = 0,
                                     int cin_total = 0, int ci_off = 0, int co_off = 0) {
   // (cin_total > 0: the partials are one 32 x 32 channel block of a wider layer's [cout][cin_total][3][3] gradient)
+  // 64 outputs per block, the slots of an output split over 4 thread quarters (a small shard of the meta-batch leaves
+  // up to 148 / tasks slots per task: a serial sum is a chain of that many L2 round trips)
+  __shared__ double part[4][64];
   if (cin_total == 0) cin_total = cin;
   const int task = blockIdx.y;
   const int per = 9 * cin * cout;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + li;
   int used = splits;
   if (ctas > 0) {
     const long long G = (long long)gridDim.y * tiles_per_task;
@@ -342,18 +346,30 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
     const int last = (int)((((long long)(task + 1) * tiles_per_task) * ctas + G - 1) / G) - 1;
     used = last - first + 1;
   }
+  double s = 0.0;
   if (i < per) {
+    const float* P = partial + (long long)task * splits * per + i;
+    int k = kq;
+    for (; k + 12 < used; k += 16) {                              // four independent loads in flight per thread
+      const float a = P[(long long)k * per], b = P[(long long)(k + 4) * per];
+      const float c = P[(long long)(k + 8) * per], d = P[(long long)(k + 12) * per];
+      s += ((double)a + (double)b) + ((double)c + (double)d);
+    }
+    for (; k < used; k += 4) s += (double)P[(long long)k * per];
+  }
+  part[kq][li] = s;
+  __syncthreads();
+  if (kq == 0 && i < per) {
+    s = (part[0][li] + part[1][li]) + (part[2][li] + part[3][li]);
     const int row = i / cout, co = i - row * cout;
     const int tap = row / cin, ci = row - tap * cin;
-    const float* P = partial + (long long)task * splits * per + i;
-    double s = 0.0;
-    for (int k = 0; k < used; ++k) s += (double)P[(long long)k * per];
     const long long o = ((long long)(co_off + co) * cin_total + ci_off + ci) * 9 + tap;
     const float b = base_w ? base_w[(long long)task * base_stride + o] : 0.f;
     out_w[(long long)task * out_stride + o] = b + scale * (float)s;
   }
-  if (out_b && i < cout)
-    out_b[(long long)task * out_stride + co_off + i] = base_b ? base_b[(long long)task * base_stride + co_off + i] : 0.f;
+  const int ib = blockIdx.x * 256 + threadIdx.x;
+  if (out_b && ib < cout)
+    out_b[(long long)task * out_stride + co_off + ib] = base_b ? base_b[(long long)task * base_stride + co_off + ib] : 0.f;
 }
 
 static void wgrad_geo(const XmBlockGeom& g, TileGeo& t) {
@@ -406,7 +422,7 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
     if (tsplits < 0) return rc;
     if (tsplits > 0) {
       const int per = 9 * 32 * 32, blocks = g.cout / 32;
-      dim3 rgrid((per + 255) / 256, g.tasks);
+      dim3 rgrid((per + 63) / 64, g.tasks);
       for (int cb = 0; cb < blocks; ++cb)
         for (int ib = 0; ib < blocks; ++ib) {
           const float* part = a->partial + (long long)(cb * blocks + ib) * g.tasks * tsplits * per;
@@ -435,7 +451,7 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
     wgrad_img_kernel<<<grid, WI_THREADS, smem, stream>>>(k);
     if (int rc = launched("xm_wgrad(image)")) return rc;
     const int per = 9 * g.cin * g.cout;
-    dim3 rgrid((per + 255) / 256, g.tasks);
+    dim3 rgrid((per + 63) / 64, g.tasks);
     wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, k.splits, g.cin, g.cout, a->out_w, a->out_b,
                                                   a->out_task_stride, a->base_w, a->base_b,
                                                   a->base_task_stride, a->scale);
@@ -469,7 +485,7 @@ extern "C" int xm_wgrad(const XmWgradArgs* a, void* stream_) {
   int rc = launched("xm_wgrad");
   if (rc) return rc;
   const int per = 9 * g.cin * g.cout;
-  dim3 rgrid((per + 255) / 256, g.tasks);
+  dim3 rgrid((per + 63) / 64, g.tasks);
   wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(a->partial, p.splits, g.cin, g.cout, a->out_w, a->out_b,
                                                 a->out_task_stride, a->base_w, a->base_b, a->base_task_stride,
                                                 a->scale);
