@@ -20,11 +20,12 @@
 //
 // Precision: parity is stated in fp32, so every product is evaluated as a 3-term TF32 expansion
 // (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi; hi = rna_tf32(x), lo = x - hi): the producer warps split the activations
-// while staging.  The three kw taps are stacked in N (columns kw*32 + cout) and so are the hi / lo weights: per kernel
-// row kh and channel octet the MMA thread issues hi x [hi | lo] as ONE tcgen05.mma (kind::tf32, M = 128, N = 192,
-// K = 8) and lo x hi as a second one (N = 96) onto the correction columns -- 24 MMAs per tile.  The tensor core adds
-// into fp32 accumulators with truncation, so the small correction terms get their own 96 TMEM columns next to the
-// hi*hi ones and the drain sums the two with round-to-nearest adds.
+// while staging.  The three kw taps are stacked in N (columns kw*32 + cout): per kernel row kh and channel octet the
+// MMA thread issues three tcgen05.mma (kind::tf32, M = 128, N = 96, K = 8) -- 36 per tile -- into ONE 96-column TMEM
+// accumulator.  The tensor core truncates when it adds, so the 24 small correction products are issued first (they
+// sum among themselves) and the 12 hi*hi products go on top: the corrections lose at most one rounding.
+// (Stacking the hi and lo weights in N = 192 -- 24 MMAs per tile into two accumulators -- is equivalent in time:
+// an MMA's floor is proportional to N)
 //
 // FP16-split variant (template parameter F16, xm_set_precision(2)): the same 3-term expansion on kind::f16 -- twice the
 // tensor rate of kind::tf32 and half the shared-memory bytes per element, the two things that bound this kernel.
@@ -43,7 +44,7 @@
 // elected lane of warp 7 issues the MMAs, warps 8-11 and 12-15 are two drain groups working on alternate tiles
 // (warp w reads TMEM lane quarter w%4: tcgen05.ld -> kw shift-add across lanes -> the warp's 32 finished rows staged in
 // 4 KB of its own shared memory -> read back transposed: 8 lanes per row for coalesced NHWC stores, lane = channel for
-// the BatchNorm column sums).  Two shared-memory stages and two TMEM accumulator sets; mbarrier full/free handshakes;
+// the BatchNorm column sums).  Two shared-memory stages and four TMEM accumulator sets; mbarrier full/free handshakes;
 // tcgen05.commit signals completion.  Measured (XM_TC_TIMING, scripts/gpu_tc_timing.sh, scripts/gpu_conv_elim.sh;
 // DESIGN.md section 8): every role alone needs 115-140 us of the 42x42 forward's 166 us.
 // 64-channel and stride-2 layers reuse this kernel through channel-block / full-resolution passes (conv_tc_try).
@@ -66,9 +67,10 @@ constexpr int TC_GROUPS = XM_TC_GROUPS;          // drain groups: group g drains
 constexpr int TC_THREADS = TC_PRODUCERS + 32 + TC_GROUPS * TC_DRAINERS;
 constexpr int TC_STG_BYTES = 32 * 128 + 32 * 8;   // per drain WARP: its 32 accumulator rows (128 B each, chunks XOR-swizzled) + 32 output offsets
 constexpr int TC_TILE = 126;          // outputs per tile: 128 accumulator rows minus the two shifted-out rows
-constexpr int TC_TMEM_COLS = 512;     // 2 sets x 2 accumulators x 96 columns = 384 -> next power of two
+constexpr int TC_SETS = 4;            // TMEM accumulator sets: tile it -> set it % 4 (drained by group it % G; G divides 4)
+constexpr int TC_TMEM_COLS = 512;     // 4 sets x 96 columns = 384 -> next power of two
+static_assert(TC_SETS % TC_GROUPS == 0, "a TMEM set must always be drained by the same group");
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(128, 96, 0, 0);   // A and B K-major, N = 3 taps x 32 channels
-constexpr uint32_t TC_IDESC2 = umma_idesc_tf32(128, 192, 0, 0); // N = [hi weights | lo weights]: two expansion terms per A read
 // kind::f16: fp16 inputs (a_format = b_format = 0), fp32 accumulate
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // M = 128, N = 32 (one tap)
 constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
@@ -153,22 +155,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   int* b_exp = reinterpret_cast<int*>(wmax + 1);                         // [1]
   uint64_t* mxbars = reinterpret_cast<uint64_t*>(smax + 12);             // [2] "every producer warp has posted its tile maximum"
   const uint32_t bar_max = smem_u32(mxbars);
-  // "accumulators of a tile complete": ONE BARRIER PER DRAIN GROUP (tile it -> barrier it % G, phase it / G).  A group
-  // sees every phase of its own barrier, and the barrier can run at most one phase ahead of the group (the MMAs of tile
-  // it + G need the TMEM set that tile it + G - 2 releases, which needs tile it's set released first), so the parity
-  // wait is unambiguous -- per-set barriers are not: a group would see only every G-th phase of them.
+  // "accumulators of a tile complete": ONE BARRIER PER TMEM SET (tile it -> set it % 4, phase it / 4).  A set is always
+  // drained by the same group (G divides 4), which therefore sees every phase of the set's barrier in order, and the
+  // barrier cannot run two phases ahead of it (the MMAs of tile it + 4 need the set that tile it's drain releases) -- so
+  // the parity wait is unambiguous.  Four sets let the MMAs run up to three tiles ahead of a drain group.
   const uint32_t bar_tfull = smem_u32(mxbars + 2);
-  unsigned char* stg_base = reinterpret_cast<unsigned char*>(mxbars + 2 + TC_GROUPS + (TC_GROUPS & 1));   // 16-byte aligned
-  const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfree = smem_u32(bars + 6);
+  unsigned char* stg_base = reinterpret_cast<unsigned char*>(mxbars + 2 + TC_SETS);   // 16-byte aligned
+  const uint32_t bar_full = smem_u32(bars), bar_sfree = smem_u32(bars + 2), bar_tfree = smem_u32(bars + 4);   // [4]
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full + 8 * s, TC_PRODUCERS);
       mbar_init(bar_sfree + 8 * s, 1);
-      mbar_init(bar_tfree + 8 * s, TC_DRAINERS);
       if (F16) mbar_init(bar_max + 8 * s, TC_PRODUCERS / 32);
     }
-    for (int g = 0; g < TC_GROUPS; ++g) mbar_init(bar_tfull + 8 * g, 1);
+    for (int g = 0; g < TC_SETS; ++g) { mbar_init(bar_tfull + 8 * g, 1); mbar_init(bar_tfree + 8 * g, TC_DRAINERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 7) {
@@ -204,10 +205,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_full + 8 * s, TC_PRODUCERS);
         mbar_init(bar_sfree + 8 * s, 1);
-        mbar_init(bar_tfree + 8 * s, TC_DRAINERS);
         if (F16) mbar_init(bar_max + 8 * s, TC_PRODUCERS / 32);
       }
-      for (int g = 0; g < TC_GROUPS; ++g) mbar_init(bar_tfull + 8 * g, 1);
+      for (int g = 0; g < TC_SETS; ++g) { mbar_init(bar_tfull + 8 * g, 1); mbar_init(bar_tfree + 8 * g, TC_DRAINERS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -245,11 +245,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         reinterpret_cast<__half*>(Bhi)[idx] = h;
         reinterpret_cast<__half*>(Blo)[idx] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
       } else {
-        // B[kh][c4][n2][4]: rows n2 < 96 = hi weights, n2 >= 96 = lo weights (one N = 192 operand slab)
-        const int idx = (((kh * 8 + (k >> 2)) * 192) + kw * 32 + n) * 4 + (k & 3);
+        const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
         const float hi = __uint_as_float(f2tf32(v));
         Bhi[idx] = hi;
-        Bhi[idx + 96 * 4] = v - hi;
+        Blo[idx] = v - hi;
       }
     }
   }
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     long long t_wait = 0, t_tmem = 0, t_rest = 0, t0, t_bar = 0, t_fix = 0, t_store = 0, t_stat = 0;
 #endif
     for (int it = group; it < ntiles; it += TC_GROUPS) {
-      const int s = it & 1;
+      (void)0;
 #ifdef XM_TC_TIMING
       t0 = clock64();
 #endif
@@ -407,28 +406,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       // tangent statistics multiply by one 128 B aux row per accumulator row: pull it into L1 while the warp waits
       // for the accumulators, so the loads in the epilogue do not expose HBM latency inside the drain
       if (p.stat_mode == XM_STAT_SUM_AUX && valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.aux + o));
-      mbar_wait(bar_tfull + 8 * group, (it / TC_GROUPS) & 1);
+      const int s4 = it & (TC_SETS - 1);
+      mbar_wait(bar_tfull + 8 * s4, (it / TC_SETS) & 1);
 #ifdef XM_TC_TIMING
       t_wait += clock64() - t0; t0 = clock64();
 #endif
       tc_fence_after();
       const int xslot = group * 2 + ((it / TC_GROUPS) & 1);       // boundary-row exchange: two alternating slots per group
       const float unscale = F16 ? exp2i(-(a_exp[it & 3] + *b_exp)) : 1.f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * (F16 ? 64 : 192));
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s4 * (F16 ? 64 : 96));
       // ---- TMEM phase: both 16-column halves -> registers (kw shifts applied), then the set is released --------
       auto load_half = [&](int half, float (&acc)[16]) {
-        // one 16-column block at a time (register pressure): kw = 1, kw = 2, then the thread's own kw = 0 block
+        // the three kw blocks of this half: all loads in flight, one wait; then kw = 1, kw = 2 and the thread's own kw = 0
         float* xb = xch + (((xslot * 2 + half) * 4 + quarter) * 3) * 16;
+        uint32_t r[3][16];
+        tmem_ld16_nowait(taddr + 32 + half * 16, r[1]);
+        tmem_ld16_nowait(taddr + 64 + half * 16, r[2]);
+        tmem_ld16_nowait(taddr + half * 16, r[0]);
+        tmem_ld_wait();
 #pragma unroll
         for (int blk = 1; blk <= 3; ++blk) {
           const int kw = blk % 3;                                  // 1, 2, 0
-          uint32_t r1[16], r2[16];
           float v[16];
-          tmem_ld16_nowait(taddr + 96 + kw * 32 + half * 16, r1);  // correction terms (small)
-          tmem_ld16_nowait(taddr + kw * 32 + half * 16, r2);       // hi*hi terms
-          tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[kw][k]);
           if (kw == 1) {
             // boundary rows for the previous warp: lane 0 publishes its kw = 1 block
             if (lane == 0) {
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         load_half(1, acc2[1]);
       }
       tc_fence_before();
-      mbar_arrive(bar_tfree + 8 * s);                            // TMEM set s may be overwritten
+      mbar_arrive(bar_tfree + 8 * s4);                           // this TMEM set may be overwritten
 #ifdef XM_TC_TIMING
       t_tmem += clock64() - t0; t0 = clock64();
 #endif
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   } else {
     // ======================================= MMA issuer =================================================
     // per tile: for every kernel row kh and channel octet ks, ONE A tile (the halo at row offset kh*Wp) against
-    // the [8 x 192] slab of the three kw taps' hi and lo weights; 3 expansion terms in 2 MMAs -> 24 per tile.
+    // the [8 x 96] weight slab of the three kw taps; 3 expansion terms -> 36 MMAs (M=128, N=96, K=8).
 #ifdef XM_TC_TIMING
     long long t_wf = 0, t_wt = 0, t_issue = 0, t0;
     unsigned long long ns0, ns1;
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t_wf += clock64() - t0; t0 = clock64();
 #endif
-      if (it >= 2) mbar_wait(bar_tfree + 8 * s, ((it - 2) >> 1) & 1);
+      const int s4 = it & (TC_SETS - 1);
+      if (it >= TC_SETS) mbar_wait(bar_tfree + 8 * s4, (it / TC_SETS - 1) & 1);
 #ifdef XM_TC_TIMING
       t_wt += clock64() - t0; t0 = clock64();
 #endif
@@ -610,9 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       if (elect_one_sync()) {
         // descriptor low words (start address | LBO) of the stage; per MMA only the start field moves
         const uint32_t a_base = smem_u32(Abase + (size_t)(2 * s) * set_bytes);
-        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 192u * 16u);
+        const uint32_t b_hi0 = umma_desc_lo(smem_u32(Bhi), 96u * 16u), b_lo0 = umma_desc_lo(smem_u32(Blo), 96u * 16u);
         constexpr uint32_t dhi = umma_desc_hi(128u);
-        const uint32_t d0 = tmem_base + (uint32_t)(s * 192);
+        const uint32_t d0 = tmem_base + (uint32_t)(s4 * 96);
         const uint32_t a_hi0 = umma_desc_lo(a_base, (uint32_t)plane);
         const uint32_t a_lo0 = a_hi0 + (uint32_t)(set_bytes >> 4);
         const uint32_t kstep = (uint32_t)(2 * plane) >> 4;          // two channel-group planes per K = 8
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           // staged halo at row offset kh*Wp + kw, so all nine taps accumulate into the SAME 32 columns: accumulator row i
           // is output position q0 + i, and the drain needs no cross-lane kw shift-add (54 MMAs, 2 x 32 TMEM columns).
           const uint32_t bf_hi0 = umma_desc_lo(smem_u32(Bhi), 32u * 16u), bf_lo0 = umma_desc_lo(smem_u32(Blo), 32u * 16u);
-          const uint32_t df = tmem_base + (uint32_t)(s * 64);
+          const uint32_t df = tmem_base + (uint32_t)(s4 * 64);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3));
@@ -635,28 +637,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
               umma_f16_lh(df, a_hi0 + ao, dhi, bf_hi0 + bo, dhi, TC_IDESC_F16, acc);
             }
           }
-        } else
+        } else {
+          // ONE accumulator per tile (96 columns: four TMEM sets instead of two).  The tensor core truncates when it adds,
+          // so the 24 small correction products are summed FIRST, among themselves, and the 12 hi*hi products go on top:
+          // the corrections then lose at most the one rounding that the drain's separate add used to cost.
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const uint32_t shift = (uint32_t)(kh * p.Wp);             // 16 B units (one staged row = 16 B per plane)
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t shift = (uint32_t)(kh * p.Wp);           // 16 B units (one staged row = 16 B per plane)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t ao = shift + (uint32_t)ks * kstep;
-            const uint32_t bo = (uint32_t)((kh * 8 + 2 * ks) * 192);  // 16 B units, compile-time
-#ifdef XM_TC_NOMMA
-            if (kh == 0 && ks == 0) {
-#endif
-            // hi x [hi | lo] in ONE MMA (N = 192: columns [0, 96) hi*hi, [96, 192) hi*lo), then lo x hi onto the
-            // correction columns: 17 KB of operand reads per K step instead of 21 KB, 24 MMAs per tile instead of 36
-            umma_tf32_lh(d0, a_hi0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC2, (uint32_t)((kh | ks) != 0));
-            umma_tf32_lh(d0 + 96, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, 1u);
-#ifdef XM_TC_NOMMA
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ao = shift + (uint32_t)ks * kstep;
+              const uint32_t bo = (uint32_t)((kh * 8 + 2 * ks) * 96);   // 16 B units, compile-time
+              umma_tf32_lh(d0, a_lo0 + ao, dhi, b_hi0 + bo, dhi, TC_IDESC, (uint32_t)((kh | ks) != 0));
+              umma_tf32_lh(d0, a_hi0 + ao, dhi, b_lo0 + bo, dhi, TC_IDESC, 1u);
             }
+          }
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t shift = (uint32_t)(kh * p.Wp);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#ifdef XM_TC_NOMMA
+              if (kh | ks) continue;
 #endif
+              umma_tf32_lh(d0, a_hi0 + shift + (uint32_t)ks * kstep, dhi, b_hi0 + (uint32_t)((kh * 8 + 2 * ks) * 96), dhi, TC_IDESC, 1u);
+            }
           }
         }
         umma_commit(bar_sfree + 8 * s);     // shared-memory stage s consumed
-        umma_commit(bar_tfull + 8 * (it % TC_GROUPS));     // accumulators of this tile complete: its drain group's barrier
+        umma_commit(bar_tfull + 8 * s4);    // accumulators of this tile complete
       }
       __syncwarp();
 #ifdef XM_TC_TIMING
@@ -688,7 +697,7 @@ static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes, bool f16) {
   plane_bytes = rpad * 16;
   const int nplanes = f16 ? 4 : 8, bwords = f16 ? 3 * 4 * 96 * 4 : 3 * 8 * 96 * 4;
   return (size_t)2 * bwords * 4 + (size_t)4 * nplanes * plane_bytes + 10 * 8 + (size_t)TC_GROUPS * 2 * 2 * 4 * 3 * 16 * 4 + 16 * 4 + 2 * 8 +
-         (TC_GROUPS + (TC_GROUPS & 1)) * 8 + (size_t)TC_GROUPS * 4 * TC_STG_BYTES;
+         TC_SETS * 8 + (size_t)TC_GROUPS * 4 * TC_STG_BYTES;
 }
 
 // Returns 1 if the call was handled by the tcgen05 path, 0 if the shape is not covered (caller falls back),
