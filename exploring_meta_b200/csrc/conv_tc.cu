@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     const float* wst = reinterpret_cast<const float*>(wst4);
     long long* wso = reinterpret_cast<long long*>(wst4 + 32 * 8);
 #ifdef XM_TC_TIMING
-    long long t_wait = 0, t_tmem = 0, t_rest = 0, t0, t_bar = 0, t_fix = 0, t_store = 0, t_stat = 0;
+    long long t_wait = 0, t_tmem = 0, t_rest = 0, t0, t_bar = 0, t_store = 0, t_stat = 0;
 #endif
     for (int it = group; it < ntiles; it += TC_GROUPS) {
       (void)0;
@@ -481,36 +481,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #ifdef XM_TC_TIMING
       t_tmem += clock64() - t0; t0 = clock64();
 #endif
-      if (!F16) asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");   // the group's four warps: boundary rows published
-#ifdef XM_TC_TIMING
-      t_bar += clock64() - t0; t0 = clock64();
-#endif
-      if (!F16 && lane >= 30) {
-        // xn = next warp's published rows: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
-        // (16-byte loads of BOTH halves issued before the first use: one shared-memory round trip instead of 96)
-        float4 a[2][4], b[2][4];
-        const int oa = lane == 31 ? 0 : 4;                       // lane 31: kw=1 of row +1; lane 30: kw=2 of row +2
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const float4* xn = reinterpret_cast<const float4*>(xch + (((xslot * 2 + half) * 4 + ((quarter + 1) & 3)) * 3) * 16);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { a[half][k] = xn[oa + k]; b[half][k] = xn[8 + k]; }
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 z = lane == 31 ? b[half][k] : make_float4(0.f, 0.f, 0.f, 0.f);   // lane 31 adds kw=2 of row +2 (lane 1)
-            acc2[half][4 * k] += a[half][k].x + z.x; acc2[half][4 * k + 1] += a[half][k].y + z.y;
-            acc2[half][4 * k + 2] += a[half][k].z + z.z; acc2[half][4 * k + 3] += a[half][k].w + z.w;
-          }
-        }
-      }
-#ifdef XM_TC_TIMING
-      __syncwarp();
-      t_fix += clock64() - t0; t0 = clock64();
-#endif
       // ---- epilogue: rows -> per-warp staging -> coalesced stores (or vector reductions) and the statistics --------
+      // Rows 30 and 31 of a warp still miss the kw = 1 / kw = 2 terms that sit in the NEXT warp's lanes 0 and 1 (published
+      // in xch above).  They are staged as they are; the readers below add the missing terms to those two rows after the
+      // group barrier -- no separate fix-up round trip through shared memory.
       __syncwarp();                                              // the previous tile's reads of the staging are complete
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -518,7 +492,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         wst4[lane * 8 + (k ^ (lane & 7))] = valid ? make_float4(a4[0], a4[1], a4[2], a4[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       wso[lane] = valid ? o : -1ll;
-      __syncwarp();
+      // the group's four warps: boundary rows published (and this warp's staging complete)
+      if (!F16) asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+      else __syncwarp();
+#ifdef XM_TC_TIMING
+      t_bar += clock64() - t0; t0 = clock64();
+#endif
+      // xn = next warp's published rows of a half: [0..15] lane 0 kw=1, [16..31] lane 0 kw=2, [32..47] lane 1 kw=2
+      //   row 31 += lane 0's kw=1 block + lane 1's kw=2 block;   row 30 += lane 0's kw=2 block
+      const float* xn0 = xch + (((xslot * 2 + 0) * 4 + ((quarter + 1) & 3)) * 3) * 16;
+      const float* xn1 = xch + (((xslot * 2 + 1) * 4 + ((quarter + 1) & 3)) * 3) * 16;
 #ifndef XM_TC_NOSTORE
       {
         const int c = lane & 7, rsub = lane >> 3;
@@ -529,6 +512,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
           const int r = 4 * k + rsub;
           v[k] = wst4[r * 8 + (c ^ (r & 7))];
           orow[k] = wso[r];
+        }
+        if (!F16 && rsub >= 2) {                                 // k = 7: rows 30 (rsub 2) and 31 (rsub 3)
+          const float4* xn = reinterpret_cast<const float4*>(c < 4 ? xn0 : xn1) + (c & 3);
+          const float4 e = xn[rsub == 3 ? 0 : 4];
+          const float4 f = rsub == 3 ? xn[8] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[7].x += e.x + f.x; v[7].y += e.y + f.y; v[7].z += e.z + f.z; v[7].w += e.w + f.w;
         }
         // second (src, w) pair of a call: add onto the first pass' output with fire-and-forget vector reductions
 #pragma unroll
@@ -543,10 +532,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
         // column sums over the warp's 32 rows (rows that produce no output were staged as zeros): lane = channel
         float s1 = 0.f, s2 = 0.f;
         const int cch = lane >> 2, cin4 = lane & 3;
+        float c30 = 0.f, c31 = 0.f;                              // the boundary terms of rows 30 and 31 for this channel
+        if (!F16) {
+          const float* xn = (lane < 16 ? xn0 : xn1) + (lane & 15);
+          const long long o30 = wso[30], o31 = wso[31];
+          c30 = o30 >= 0 ? xn[16] : 0.f;
+          c31 = o31 >= 0 ? xn[0] + xn[32] : 0.f;
+        }
         if (p.stat_mode == XM_STAT_SUM_SQ) {
-#pragma unroll 8
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float z = wst[j * 32 + ((cch ^ (j & 7)) << 2) + cin4];
+            float z = wst[j * 32 + ((cch ^ (j & 7)) << 2) + cin4];
+            if (j == 30) z += c30;
+            if (j == 31) z += c31;
             s1 += z;
             s2 = fmaf(z, z, s2);
           }
@@ -559,6 +557,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
               const long long orow = wso[j0 + j];
               av[j] = __ldg(p.aux + (orow >= 0 ? orow : 0ll) + lane);
               z[j] = wst[(j0 + j) * 32 + ((cch ^ ((j0 + j) & 7)) << 2) + cin4];
+              if (j0 + j == 30) z[j] += c30;
+              if (j0 + j == 31) z[j] += c31;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s1 += z[j]; s2 = fmaf(z[j], av[j], s2); }
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     t_rest = clock64() - t0;
     if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == TC_PRODUCERS + 32 || tid == TC_PRODUCERS + 32 + 127)) {
       const int nd = (ntiles - group + TC_GROUPS - 1) / TC_GROUPS;
-      printf("drainer tid %d: per DRAINED tile: wait %lld tmem %lld group-barrier %lld fix-up %lld stores %lld stats %lld\n", tid,
-             t_wait / nd, t_tmem / nd, t_bar / nd, t_fix / nd, t_store / nd, t_stat / nd);
+      printf("drainer tid %d: per DRAINED tile: wait %lld tmem %lld staging+group-barrier %lld stores %lld stats %lld\n", tid,
+             t_wait / nd, t_tmem / nd, t_bar / nd, t_store / nd, t_stat / nd);
     }
 #endif
     if (p.stat_mode) {
