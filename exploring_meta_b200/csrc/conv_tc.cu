@@ -137,6 +137,14 @@ template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef XM_TC_TIMING
+  // phase timestamps of CTA 0 / thread 0 (ns, %globaltimer), printed once at the end (a printf costs tens of microseconds)
+  unsigned long long ph_t[8]; int ph_n = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_t[0]));
+#define XM_PH(name) do { if (ph_n < 7) { ++ph_n; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_t[ph_n])); } } while (0)
+#else
+#define XM_PH(name) do { } while (0)
+#endif
   constexpr int NPLANES = F16 ? 4 : 8;            // channel-group planes of the A operand (16 B per row and plane)
   constexpr int BFLOATS = F16 ? 3 * 4 * 96 * 4    // B[kh][c8][n = kw*32 + cout][8 halfs] (4-byte words)
                               : 3 * 8 * 96 * 4;   // B[kh][c4][n = kw*32 + cout][4]
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     g_hi = (int)(G * (blockIdx.x + 1) / gridDim.x);
   }
   uint32_t tmem_base = 0;
+  XM_PH("barriers + tmem alloc issued");
   for (int gt = g_lo, seg = 0; gt < g_hi; ++seg) {
   const int task = gt / p.tiles_per_task, tile0 = gt - task * p.tiles_per_task;
   const int ntiles = min(g_hi - gt, p.tiles_per_task - tile0);   // my tiles of this task: tile0 .. tile0 + ntiles - 1
@@ -231,24 +240,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
       if (tid == 0) *b_exp = kb;
       wscale = exp2i(kb);
     }
-    for (int i = tid; i < 32 * 32 * 9; i += TC_THREADS) {
-      const int tap = i % 9, b = (i / 9) % 32, a = i / (9 * 32);   // element W[w_ao + a][w_bo + b][tap]
-      const float v = __ldg(W + ((long long)(p.w_ao + a) * p.w_cin + p.w_bo + b) * 9 + tap);
-      int n, k, t2;
-      if (p.wmode == 0) { n = a; k = b; t2 = tap; }           // forward: n = cout, k = cin
-      else { n = b; k = a; t2 = 8 - tap; }                    // dgrad: n = cin (output), k = cout, flipped taps
-      const int kh = t2 / 3, kw = t2 - 3 * kh;
-      if (F16) {
-        const int idx = ((((kh * 3 + kw) * 4 + (k >> 3)) * 32) + n) * 8 + (k & 7);   // B[tap][c8][n][8 halfs]
-        const float x = v * wscale;
-        const __half h = __float2half_rn(x);
-        reinterpret_cast<__half*>(Bhi)[idx] = h;
-        reinterpret_cast<__half*>(Blo)[idx] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
-      } else {
-        const int idx = (((kh * 8 + (k >> 2)) * 96) + kw * 32 + n) * 4 + (k & 3);
+    // Threads walk the DESTINATION linearly (consecutive lanes -> consecutive shared-memory words: conflict-free stores;
+    // walking the source instead puts the 32 lanes of a store into 4 banks) and gather the source element through L2.
+    const float* Wb = W + ((long long)p.w_ao * p.w_cin + p.w_bo) * 9;      // W[w_ao + a][w_bo + b][tap] = Wb[(a * w_cin + b) * 9 + tap]
+    if (F16) {
+      // B[tap][k/8][n][k%8] halfs, two consecutive k per 4-byte store
+      for (int j = tid; j < 32 * 32 * 9 / 2; j += TC_THREADS) {
+        const int k2 = j & 3, n = (j >> 2) & 31, g = j >> 7;                // g = tap * 4 + k/8
+        const int t2 = g >> 2, k = (g & 3) * 8 + 2 * k2;
+        int aa, bb, tap;
+        if (p.wmode == 0) { aa = n; bb = k; tap = t2; } else { bb = n; aa = k; tap = 8 - t2; }
+        const int step = p.wmode == 0 ? 9 : p.w_cin * 9;                     // k -> k + 1 in the source
+        const float* src = Wb + ((long long)aa * p.w_cin + bb) * 9 + tap;
+        const float x0 = __ldg(src) * wscale, x1 = __ldg(src + step) * wscale;
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 back = __half22float2(h);
+        reinterpret_cast<__half2*>(Bhi)[j] = h;
+        reinterpret_cast<__half2*>(Blo)[j] = __floats2half2_rn((x0 - back.x) * LO_SCALE, (x1 - back.y) * LO_SCALE);
+      }
+    } else {
+      // B[kh][k/4][n = kw*32 + out channel][k%4] floats
+#pragma unroll 9
+      for (int j = tid; j < 32 * 32 * 9; j += TC_THREADS) {
+        const int k4 = j & 3, n96 = (j >> 2) % 96, g = j / 384;             // g = kh * 8 + k/4
+        const int kh = g >> 3, k = (g & 7) * 4 + k4, kw = n96 >> 5, n = n96 & 31, t2 = kh * 3 + kw;
+        int aa, bb, tap;
+        if (p.wmode == 0) { aa = n; bb = k; tap = t2; }                     // forward: n = cout, k = cin
+        else { bb = n; aa = k; tap = 8 - t2; }                              // dgrad: n = cin (output), k = cout, flipped taps
+        const float v = __ldg(Wb + ((long long)aa * p.w_cin + bb) * 9 + tap);
         const float hi = __uint_as_float(f2tf32(v));
-        Bhi[idx] = hi;
-        Blo[idx] = v - hi;
+        Bhi[j] = hi;
+        Blo[j] = v - hi;
       }
     }
   }
@@ -257,6 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
   __syncthreads();
   tc_fence_after();
   tmem_base = *tmem_slot;
+  XM_PH("weights staged, roles start");
 
   if (warp < 7) {
     // ========================================= producers =============================================
@@ -364,6 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     for (int it = 0; it < ntiles; it += 2) {
       if (it + 1 < ntiles) XM_T_ISS(issue_loads(it + 1, vb));
       store_tile(it, va);
+      if (it == 0) XM_PH("first tile staged");
       if (it + 1 < ntiles) {
         if (it + 2 < ntiles) XM_T_ISS(issue_loads(it + 2, va));
         store_tile(it + 1, vb);
@@ -681,6 +705,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
 #endif
   }
 
+  tc_fence_before();
+  __syncthreads();
+  XM_PH("segment done (all roles)");
   }   // segments
 
   tc_fence_before();
@@ -689,6 +716,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvTcK p)
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
+  XM_PH("kernel end");
+#ifdef XM_TC_TIMING
+  if (blockIdx.x == 0 && tid == 0) {
+    printf("phases (ns since entry): alloc issued, [weights staged, first tile staged, segment done]*, end:");
+    for (int i = 1; i <= ph_n; ++i) printf(" %llu", ph_t[i] - ph_t[0]);
+    printf("\n");
+  }
+#endif
 }
 
 static size_t conv_tc_smem(int Wp, int& R, int& plane_bytes, bool f16) {
