@@ -192,3 +192,50 @@ def fast_adapt_ppo(task, learner, baseline, params, anil=False, render=False):
     valid_loss = _PpoValidLoss.apply(valid[0], grad, *before)
     query_rew = query['rewards'].sum().item() / params['adapt_batch_size']
     return valid_loss, query_rew, 0.0
+
+
+def vpg_a2c_loss(episodes, learner, baseline, gamma, tau, dice=False):
+    """rl.py:208-226, value only: ``a2c.policy_loss`` of ``learner`` on ``episodes`` against the raw (un-normalised) GAE
+    advantages of the baseline re-fitted on these episodes."""
+    if dice:
+        raise NotImplementedError('the DiCE objective is not on the built path')
+    rep = _as_dict(episodes)
+    dev = _device_of(learner)
+    e = _engine(learner, baseline, 1, rep['states'].shape[0], 0.0, gamma, tau, dev)
+    e.load_replays([[rep, rep]], normalize=False)
+    return e.a2c_loss(learner.flat_parameters().to(dev))[0]
+
+
+def fast_adapt_vpg(task, learner, baseline, params, anil=False, first_order=False, render=False):
+    """rl.py:229-254.  ``learner`` = ``policy.clone()`` of a ``MAML``-wrapped ``DiagNormalPolicy`` /
+    ``DiagNormalPolicyANIL``; ``task.run(learner, episodes=...)`` collects the replays (environment side,
+    caller-provided).  Returns ``(valid_loss, query_rew, query_success_rate)``; ``valid_loss.backward()`` accumulates the
+    (second-order unless ``first_order``) meta-gradient into the master policy like the reference's autograd graph."""
+    if params.get('adapt_steps', 1) != 1:
+        raise NotImplementedError('one adaptation step (one support replay) per task')
+    policy = learner.module
+    before = list(policy.parameters())                       # the clone's differentiable copies of the master
+    dev = before[0].device
+    theta0 = torch.cat([p.detach().reshape(-1).float() for p in before])
+    if anil:
+        policy.turn_off_body_grads()
+    support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
+    lr = getattr(learner, 'lr', params.get('inner_lr'))
+    e = _engine(policy, baseline, 1, support['states'].shape[0], lr, params['gamma'], params['tau'], dev)
+    e.load_replays([[support, support]], normalize=False)
+    adapted = e.adapt(theta0, head_only=1 if anil else 0)[0].clone()
+    # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the query rollouts
+    o = 0
+    for module in policy.modules():
+        for name, p in list(module._parameters.items()):
+            if p is not None:
+                module._parameters[name] = adapted[o:o + p.numel()].view_as(p)
+                o += p.numel()
+    if anil:
+        policy.turn_on_body_grads()
+    query = _as_dict(task.run(learner, episodes=params['adapt_batch_size']))
+    e.load_replays([[support, query]], normalize=False)
+    valid, grad, _adapted = e.vpg_meta_gradient(theta0, anil=anil, first_order=first_order)
+    valid_loss = _PpoValidLoss.apply(valid[0], grad, *before)
+    query_rew = query['rewards'].sum().item() / params['adapt_batch_size']
+    return valid_loss, query_rew, 0.0

@@ -72,9 +72,10 @@ class TrpoEngine:
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
 
     # ---- inputs ---------------------------------------------------------------------------------------------------------
-    def load_replays(self, replays):
+    def load_replays(self, replays, normalize=True):
         """replays: list (tasks) of [support, query] dicts with keys states / actions / rewards / dones / next_states
-        (``exploring_meta_b200.synthetic.make_replays``) -- or objects with cherry's ExperienceReplay accessors."""
+        (``exploring_meta_b200.synthetic.make_replays``) -- or objects with cherry's ExperienceReplay accessors.
+        ``normalize=False``: loss weights from the raw GAE advantages (``vpg_a2c_loss``, rl.py:208-226)."""
         def field(rep, key):
             if isinstance(rep, dict):
                 return rep[key]
@@ -84,19 +85,26 @@ class TrpoEngine:
             for key, dst in zip(KEYS, (self.states, self.actions, self.rewards, self.dones, self.next_states)):
                 stacked = torch.stack([field(task[k], key).reshape(dst.shape[2:]).float() for task in replays])
                 dst[k].copy_(stacked, non_blocking=True)
-        self.prepare()
+        self.prepare(normalize)
 
-    def prepare(self):
-        """Normalised advantages of every replay -> per-sample loss weights (once per meta-optimisation):
+    def prepare(self, normalize=True):
+        """Advantages of every replay -> per-sample loss weights (once per meta-optimisation):
         support: -adv / n  (a2c.policy_loss, rl.py:358);  query: -adv / (n * tasks)  (trpo.policy_loss + the mean over
-        tasks, rl.py:469-472)."""
+        tasks, rl.py:469-472).  adv = the normalised GAE advantages (``ch.normalize``, rl.py:355) or, with
+        ``normalize=False``, the raw ones (``vpg_a2c_loss`` does not normalise, rl.py:208-226)."""
+        if not normalize and getattr(self, 'adv_raw', None) is None:
+            self.adv_raw = torch.zeros(2, self.tasks, self.n, dtype=torch.float32, device=self.device)
         for k, scale in ((0, -1.0 / self.n), (1, -1.0 / (self.n * self.total_tasks))):
             a = XmRlAdvArgs()
             a.replays, a.n, a.state_dim = self.tasks, self.n, self.sd
             a.gamma, a.tau, a.reg, a.coef_scale = self.gamma, self.tau, self.reg, scale
             a.states, a.next_states = _p(self.states[k]), _p(self.next_states[k])
             a.rewards, a.dones, a.coef = _p(self.rewards[k]), _p(self.dones[k]), _p(self.coef[k])
+            if not normalize:
+                a.advantages = _p(self.adv_raw[k])
             _lib.check(self.lib.xm_rl_advantages(ctypes.byref(a), self._stream()), 'xm_rl_advantages')
+            if not normalize:
+                torch.mul(self.adv_raw[k], scale, out=self.coef[k])      # the kernel's raw-advantage output, rescaled
 
     # ---- sweeps -----------------------------------------------------------------------------------------------------------
     def _sweep_args(self, loss, what, k):
@@ -112,14 +120,16 @@ class TrpoEngine:
     def _launch(self, a):
         _lib.check(self.lib.xm_rl_sweep(ctypes.byref(a), self._stream()), 'xm_rl_sweep')
 
-    def adapt(self, theta, out=None, stride=0):
+    def adapt(self, theta, out=None, stride=0, head_only=0):
         """theta'_t = theta_t - lr * grad_theta [ -mean(log_prob * adv) ] on the support replay: ``trpo_update``
-        (rl.py:361-374) for every task.  ``theta`` [P] shared (stride 0) or [tasks, P]."""
+        (rl.py:361-374) for every task.  ``theta`` [P] shared (stride 0) or [tasks, P].  ``head_only=1``: the ANIL
+        policy (body frozen in the inner loop)."""
         out = self.theta_prime if out is None else out
         a = self._sweep_args(XM_RL_A2C, XM_RL_GRAD, 0)
         a.theta, a.theta_task_stride = _p(theta), stride
         a.out, a.out_task_stride = _p(out), self.P
         a.base, a.base_task_stride, a.scale = _p(theta), stride, -self.lr
+        a.head_only = head_only
         self._launch(a)
         return out
 
@@ -131,13 +141,15 @@ class TrpoEngine:
         self._launch(a)
         return self.task_loss if k == 0 else self.task_loss * self.total_tasks
 
-    def hvp(self, theta, v, v_stride, out):
-        """out_t = v_t - lr * H_t(theta) v_t: the cotangent (or tangent -- H is symmetric) through the adaptation step."""
+    def hvp(self, theta, v, v_stride, out, head_only=0):
+        """out_t = v_t - lr * H_t(theta) v_t: the cotangent (or tangent -- H is symmetric) through the adaptation step
+        (``head_only=3``: v_t - lr * M H_t (M v_t), the ANIL inner-loop graph holds the head / sigma only)."""
         a = self._sweep_args(XM_RL_A2C, XM_RL_HVP, 0)
         a.theta, a.theta_task_stride = _p(theta), 0
         a.theta_dot, a.theta_dot_task_stride = _p(v), v_stride
         a.out, a.out_task_stride = _p(out), self.P
         a.base, a.base_task_stride, a.scale = _p(v), v_stride, -self.lr
+        a.head_only = head_only
         self._launch(a)
         return out
 
@@ -232,6 +244,27 @@ class TrpoEngine:
         adapted = self.ppo_adapt(theta, epochs, clip, anil)
         valid, grad = self.ppo_outer(epochs, clip, anil)
         return valid, grad, adapted
+
+    # ---- MAML / ANIL - VPG (core_functions/rl.py:208-254) ---------------------------------------------------------------------
+    def vpg_meta_gradient(self, theta, anil=False, first_order=False):
+        """``fast_adapt_vpg`` for every task (one adaptation step; replays loaded with ``normalize=False``) + the gradient
+        of the mean validation loss w.r.t. the shared initial parameters ``theta`` [P]:
+        theta'_t = theta - lr * M grad L_a2c(theta; support_t)            (``learner.adapt``, rl.py:241)
+        valid_t  = L_a2c(theta'_t; query_t)                                (rl.py:250)
+        grad     = sum_t [ bar_t - lr * M H_t(theta) (M bar_t) ],  bar_t = d valid_t / d theta'_t   (``first_order``: bar_t)
+        M = identity (MAML) or the head / sigma mask (ANIL).  Returns (valid loss per task (already / total tasks),
+        gradient [P], adapted parameters [tasks, P])."""
+        P = self.P
+        adapted = self.adapt(theta, head_only=1 if anil else 0)
+        valid = self.a2c_loss(adapted, stride=P, k=1).clone() / self.total_tasks
+        a = self._sweep_args(XM_RL_A2C, XM_RL_GRAD, 1)
+        a.theta, a.theta_task_stride = _p(adapted), P
+        a.out, a.out_task_stride, a.scale = _p(self.bar), P, 1.0
+        self._launch(a)
+        if first_order:
+            return valid, self._sum_tasks(self.bar), adapted
+        self.hvp(theta, self.bar, P, self.pertask, head_only=3 if anil else 0)
+        return valid, self._sum_tasks(self.pertask), adapted
 
     def _sum_tasks(self, per_task):
         out = torch.empty(self.P, dtype=torch.float32, device=self.device)

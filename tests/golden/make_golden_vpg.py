@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Generates tests/golden/rl/rl_vpg_small.npz from the REFERENCE'S OWN FILES (build container only):
+
+    python tests/golden/make_golden_vpg.py            # needs /root/reference
+
+The train half of one MAML-VPG / ANIL-VPG outer iteration (rl/maml_vpg.py, rl/anil_vpg.py) minus the environment: per task
+``policy.clone()`` (learn2learn MAML restatement), the reference's unmodified ``core_functions/rl.py::fast_adapt_vpg``
+with a stub task whose ``run()`` returns the seeded synthetic replays, the mean validation loss, ``backward()``; second
+order and ``first_order=True``.  float64.  Before anything is written oracle/rl_oracle.py::fast_adapt_vpg must
+reproduce the run (validation losses, adapted parameters, meta-gradient)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from exploring_meta_b200.synthetic import make_replays     # noqa: E402
+from oracle import l2l_shim                                 # noqa: E402
+from oracle import rl_oracle as ro                          # noqa: E402
+from oracle import rl_ref_loader                            # noqa: E402
+
+CFG = {'inner_lr': 0.05, 'tau': 1.0, 'gamma': 0.99, 'value_reg': 2, 'adapt_steps': 1, 'adapt_batch_size': 4,
+       'max_path_length': 25}
+TASKS, EPISODES, HORIZON, SEED = 3, 4, 25, 3
+
+
+class StubTask:
+    """``task.run(learner, episodes=...)``: first call the support replay, second call the query replay."""
+    def __init__(self, ch, sup, qry):
+        mk = lambda r: ch.Replay(r['states'], r['actions'], r['rewards'], r['dones'], r['next_states'])   # noqa: E731
+        self.queue = [mk(sup), mk(qry)]
+
+    def run(self, learner, episodes=None, render=False):
+        return self.queue.pop(0)
+
+
+def main():
+    ns = rl_ref_loader.load()
+    rl, pol, ch = ns.rl, ns.policies, ns.cherry
+    rl.set_device(torch.device('cpu'))
+    rl.get_ep_successes = lambda episodes, path_length: 0          # environment bookkeeping (success flags): not on the path
+    torch.set_default_dtype(torch.float64)
+    data = make_replays(TASKS, EPISODES, HORIZON, seed=SEED, dtype=torch.float64)
+    out = {}
+    for anil in (False, True):
+        for first_order in (False, True):
+            torch.manual_seed(42)
+            policy = pol.DiagNormalPolicyANIL(2, 2, 100) if anil else pol.DiagNormalPolicy(2, 2, activation='tanh')
+            policy = policy.double()
+            policy.sigma.data += torch.tensor([0.1, -0.2])
+            theta0 = [p.detach().clone() for p in policy.parameters()]
+            maml = l2l_shim.MAML(policy, lr=CFG['inner_lr'])
+            baseline = ch.LinearValue(2, CFG['value_reg']).double()
+            losses, adapted = [], []
+            total = 0.0
+            for sup, qry in data:
+                learner = maml.clone()
+                loss, _rew, _suc = rl.fast_adapt_vpg(StubTask(ch, sup, qry), learner, baseline, CFG, anil=anil,
+                                                     first_order=first_order)
+                losses.append(float(loss))
+                adapted.append(torch.cat([p.detach().reshape(-1) for p in learner.module.parameters()]))
+                total = total + loss
+            (total / TASKS).backward()
+            grad = torch.cat([p.grad.reshape(-1) for p in policy.parameters()])
+            # ---- the restatement must reproduce the reference-file run ------------------------------------------
+            ps = [p.clone().requires_grad_() for p in theta0]
+            tot = 0.0
+            for t, (sup, qry) in enumerate(data):
+                v, new = ro.fast_adapt_vpg(ps, sup, qry, CFG, anil=anil, first_order=first_order)
+                assert abs(float(v) - losses[t]) < 1e-10 * max(1.0, abs(losses[t])), (float(v), losses[t])
+                assert torch.allclose(torch.cat([x.detach().reshape(-1) for x in new]), adapted[t], rtol=1e-10, atol=1e-12)
+                tot = tot + v
+            g_or = torch.cat([g.reshape(-1) for g in torch.autograd.grad(tot / TASKS, ps)])
+            assert torch.allclose(g_or, grad, rtol=1e-9, atol=1e-10), (g_or - grad).abs().max()
+            key = ('anil' if anil else 'maml') + ('_fo' if first_order else '')
+            out[key + '_theta0'] = torch.cat([p.reshape(-1) for p in theta0]).numpy()
+            out[key + '_adapted'] = torch.stack(adapted).numpy()
+            out[key + '_valid_loss'] = np.array(losses)
+            out[key + '_grad'] = grad.numpy()
+            print('%s: restatement == reference files; valid losses %s, |grad| %.3e'
+                  % (key, np.round(losses, 6), float(grad.norm())))
+    np.savez_compressed(os.path.join(HERE, 'rl', 'rl_vpg_small.npz'), tasks=TASKS, episodes=EPISODES, horizon=HORIZON,
+                        seed=SEED, **out)
+    print('wrote rl_vpg_small.npz')
+
+
+if __name__ == '__main__':
+    main()

@@ -211,3 +211,87 @@ def test_fast_adapt_ppo_reference_call_pattern(kdev, anil):
     (total / tasks).backward()
     grad = torch.cat([p.grad.reshape(-1) for p in policy.parameters()])
     assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
+
+
+GOLD_VPG = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'rl', 'rl_vpg_small.npz')
+VPG_CFG = {'inner_lr': 0.05, 'tau': 1.0, 'gamma': 0.99, 'value_reg': 2}
+
+
+@pytest.mark.parametrize('anil', [False, True])
+@pytest.mark.parametrize('first_order', [False, True])
+def test_vpg_adaptation_and_meta_gradient_match_reference_fixture(kdev, anil, first_order):
+    """MAML-VPG / ANIL-VPG: the reference's own fast_adapt_vpg + backward on fixed replays
+    (tests/golden/make_golden_vpg.py) against the task-batched kernels: adapted parameters after the a2c step on the RAW
+    advantages, validation losses, and the (second- or first-order) gradient of the mean validation loss."""
+    g = np.load(GOLD_VPG)
+    key = ('anil' if anil else 'maml') + ('_fo' if first_order else '')
+    tasks, n = int(g['tasks']), int(g['episodes']) * int(g['horizon'])
+    e = TrpoEngine(tasks, n, 2, 2, (100, 100), 'tanh', VPG_CFG['inner_lr'], VPG_CFG['gamma'], VPG_CFG['tau'],
+                   VPG_CFG['value_reg'], device=kdev)
+    e.load_replays(make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed'])), normalize=False)
+    t0 = torch.from_numpy(g[key + '_theta0'])
+    theta0 = t0.float().to(kdev)
+    valid, grad, adapted = e.vpg_meta_gradient(theta0, anil=anil, first_order=first_order)
+    ref_ad = torch.from_numpy(g[key + '_adapted'])
+    assert rel(adapted, ref_ad) < 1e-5
+    d, dref = adapted.cpu().double() - t0, ref_ad - t0
+    assert float((d - dref).norm()) <= 2e-4 * float(dref.norm()) + 2e-7 * float(ref_ad.norm())
+    if anil:        # the body did not move
+        body = slice(2, 2 + 200 + 100 + 10000 + 100)
+        assert torch.equal(adapted[:, body].cpu(), theta0[body].cpu().expand(tasks, -1))
+    ref_valid = torch.from_numpy(g[key + '_valid_loss']) / tasks          # the engine's losses carry the 1 / tasks of the mean
+    assert float((valid.cpu().double() - ref_valid).abs().max()) < 2e-5 * float(ref_valid.abs().max()) + 1e-7
+    assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
+
+
+@pytest.mark.parametrize('anil', [False, True])
+def test_fast_adapt_vpg_reference_call_pattern(kdev, anil):
+    """rl/maml_vpg.py / rl/anil_vpg.py with the product's modules: policy.clone(), fast_adapt_vpg on a stub task
+    returning the fixture's replays, mean loss, backward() -> master .grad == the reference's."""
+    from exploring_meta_b200.core_functions import rl as xrl
+    from exploring_meta_b200.core_functions.maml import MAML
+    from exploring_meta_b200.core_functions.policies import DiagNormalPolicy, DiagNormalPolicyANIL, LinearValue
+    g = np.load(GOLD_VPG)
+    key = 'anil' if anil else 'maml'
+    tasks = int(g['tasks'])
+    policy = (DiagNormalPolicyANIL(2, 2, 100) if anil else DiagNormalPolicy(2, 2, activation='tanh')).to(kdev)
+    policy.load_flat_parameters(torch.from_numpy(g[key + '_theta0']).float().to(kdev))
+    maml = MAML(policy, lr=VPG_CFG['inner_lr'])
+    baseline = LinearValue(2, VPG_CFG['value_reg'])
+    params = dict(VPG_CFG, adapt_steps=1, adapt_batch_size=int(g['episodes']))
+    data = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']))
+
+    class StubTask:
+        def __init__(self, sup, qry):
+            self.queue = [sup, qry]
+
+        def run(self, learner, episodes=None, render=False):
+            return self.queue.pop(0)
+
+    total = 0.0
+    for t, (sup, qry) in enumerate(data):
+        learner = maml.clone()
+        loss, _rew, _suc = xrl.fast_adapt_vpg(StubTask(sup, qry), learner, baseline, params, anil=anil)
+        assert rel(learner.module.flat_parameters(), torch.from_numpy(g[key + '_adapted'][t])) < 1e-5
+        assert abs(float(loss) - float(g[key + '_valid_loss'][t])) < 2e-5 * abs(float(g[key + '_valid_loss'][t])) + 1e-7
+        total = total + loss
+    (total / tasks).backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in policy.parameters()])
+    assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
+    # value-only entry point: vpg_a2c_loss of the un-adapted policy on a support replay == the oracle
+    sup64 = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']), dtype=torch.float64)[0][0]
+    th64 = [p.requires_grad_() for p in _unflat64(g[key + '_theta0'])]
+    lp = ro.log_prob(th64, sup64['states'], sup64['actions']) if not anil else None
+    if lp is not None:
+        ref = ch.a2c_policy_loss(lp, ro.compute_advantages(sup64, VPG_CFG['tau'], VPG_CFG['gamma'], VPG_CFG['value_reg']))
+        got = xrl.vpg_a2c_loss(data[0][0], policy, baseline, VPG_CFG['gamma'], VPG_CFG['tau'])
+        assert abs(float(got) - float(ref)) < 2e-5 * abs(float(ref)) + 1e-7
+
+
+def _unflat64(vec):
+    like = ro.init_policy(dtype=torch.float64)
+    out, o = [], 0
+    for p in like:
+        out.append(torch.as_tensor(vec[o:o + p.numel()]).view_as(p).clone())
+        o += p.numel()
+    return out
