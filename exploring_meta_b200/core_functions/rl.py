@@ -80,7 +80,8 @@ def trpo_update(episodes, learner, baseline, inner_lr, gamma, tau, anil=False, f
     """One inner step theta' = theta - inner_lr * grad(trpo_a2c_loss) written into ``learner`` (``maml_update`` mutates
     and returns the module it is given, rl.py:374)."""
     if anil:
-        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+        raise NotImplementedError('ANIL-TRPO: the reference\'s own path (rl/anil_trpo.py -> rl.py:382, `.module` on a bare '
+                                  'policy) raises before any arithmetic -- there is no behaviour to mirror (DESIGN 10)')
     rep = _as_dict(episodes)
     dev = _device_of(learner)
     e = _engine(learner, baseline, 1, rep['states'].shape[0], inner_lr, gamma, tau, dev)
@@ -119,7 +120,8 @@ def _prepare(iter_replays, iter_policies, policy, baseline, params):
 def meta_surrogate_loss(iter_replays, iter_policies, policy, baseline, params, anil):
     """(mean surrogate loss, mean KL(new || old)) over the tasks at the current ``policy`` parameters."""
     if anil:
-        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+        raise NotImplementedError('ANIL-TRPO: the reference\'s own path (rl/anil_trpo.py -> rl.py:382, `.module` on a bare '
+                                  'policy) raises before any arithmetic -- there is no behaviour to mirror (DESIGN 10)')
     e, theta = _prepare(iter_replays, iter_policies, policy, baseline, params)
     return e.loss_and_kl(theta)
 
@@ -128,7 +130,8 @@ def meta_optimize_trpo(params, policy, baseline, iter_replays, iter_policies, an
     """One TRPO meta-step: CG direction from the second-order meta-gradient and the Fisher-vector product of the KL,
     step scaling by ``max_kl``, backtracking line search; updates ``policy`` in place like the reference."""
     if anil:
-        raise NotImplementedError('the ANIL policy variant is not on the built path (SURVEY 8 f4)')
+        raise NotImplementedError('ANIL-TRPO: the reference\'s own path (rl/anil_trpo.py -> rl.py:382, `.module` on a bare '
+                                  'policy) raises before any arithmetic -- there is no behaviour to mirror (DESIGN 10)')
     e, theta = _prepare(iter_replays, iter_policies, policy, baseline, params)
     new, diag = e.meta_optimize(theta, params['max_kl'], params['ls_max_steps'], params['backtrack_factor'],
                                 params['outer_lr'])
