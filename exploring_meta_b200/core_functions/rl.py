@@ -212,33 +212,45 @@ def vpg_a2c_loss(episodes, learner, baseline, gamma, tau, dice=False):
 def fast_adapt_vpg(task, learner, baseline, params, anil=False, first_order=False, render=False):
     """rl.py:229-254.  ``learner`` = ``policy.clone()`` of a ``MAML``-wrapped ``DiagNormalPolicy`` /
     ``DiagNormalPolicyANIL``; ``task.run(learner, episodes=...)`` collects the replays (environment side,
-    caller-provided).  Returns ``(valid_loss, query_rew, query_success_rate)``; ``valid_loss.backward()`` accumulates the
-    (second-order unless ``first_order``) meta-gradient into the master policy like the reference's autograd graph."""
-    if params.get('adapt_steps', 1) != 1:
-        raise NotImplementedError('one adaptation step (one support replay) per task')
+    caller-provided), one support replay per adaptation step.  Returns ``(valid_loss, query_rew,
+    query_success_rate)``; ``valid_loss.backward()`` accumulates the (second-order unless ``first_order``) meta-gradient
+    into the master policy like the reference's autograd graph: bar_S = d valid / d theta_S on the query replay, then
+    bar_s = bar_{s+1} - lr * M H(theta_s; support_s) (M bar_{s+1}) back through the steps."""
     policy = learner.module
     before = list(policy.parameters())                       # the clone's differentiable copies of the master
     dev = before[0].device
-    theta0 = torch.cat([p.detach().reshape(-1).float() for p in before])
+    thetas = [torch.cat([p.detach().reshape(-1).float() for p in before])]
+    lr = getattr(learner, 'lr', params.get('inner_lr'))
     if anil:
         policy.turn_off_body_grads()
-    support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
-    lr = getattr(learner, 'lr', params.get('inner_lr'))
-    e = _engine(policy, baseline, 1, support['states'].shape[0], lr, params['gamma'], params['tau'], dev)
-    e.load_replays([[support, support]], normalize=False)
-    adapted = e.adapt(theta0, head_only=1 if anil else 0)[0].clone()
-    # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the query rollouts
-    o = 0
-    for module in policy.modules():
-        for name, p in list(module._parameters.items()):
-            if p is not None:
-                module._parameters[name] = adapted[o:o + p.numel()].view_as(p)
-                o += p.numel()
+    supports, e = [], None
+    for _step in range(params.get('adapt_steps', 1)):
+        support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
+        supports.append(support)
+        e = _engine(policy, baseline, 1, support['states'].shape[0], lr, params['gamma'], params['tau'], dev)
+        e.load_replays([[support, support]], normalize=False)
+        adapted = e.adapt(thetas[-1], head_only=1 if anil else 0)[0].clone()
+        thetas.append(adapted)
+        # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the next rollouts
+        o = 0
+        for module in policy.modules():
+            for name, p in list(module._parameters.items()):
+                if p is not None:
+                    module._parameters[name] = adapted[o:o + p.numel()].view_as(p)
+                    o += p.numel()
     if anil:
         policy.turn_on_body_grads()
     query = _as_dict(task.run(learner, episodes=params['adapt_batch_size']))
-    e.load_replays([[support, query]], normalize=False)
-    valid, grad, _adapted = e.vpg_meta_gradient(theta0, anil=anil, first_order=first_order)
-    valid_loss = _PpoValidLoss.apply(valid[0], grad, *before)
+    e.load_replays([[supports[-1], query]], normalize=False)
+    P = e.P
+    valid = e.a2c_loss(thetas[-1], stride=0, k=1)[0].clone()
+    cur, nxt = e.a2c_grad(thetas[-1], 0, 1, e.bar), e.pertask
+    if not first_order:
+        for s in reversed(range(len(supports))):
+            if s != len(supports) - 1:
+                e.load_replays([[supports[s], query]], normalize=False)
+            e.hvp(thetas[s], cur, P, nxt, head_only=3 if anil else 0)
+            cur, nxt = nxt, cur
+    valid_loss = _PpoValidLoss.apply(valid, cur[0].clone(), *before)
     query_rew = query['rewards'].sum().item() / params['adapt_batch_size']
     return valid_loss, query_rew, 0.0

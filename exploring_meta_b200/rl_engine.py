@@ -257,14 +257,20 @@ class TrpoEngine:
         P = self.P
         adapted = self.adapt(theta, head_only=1 if anil else 0)
         valid = self.a2c_loss(adapted, stride=P, k=1).clone() / self.total_tasks
-        a = self._sweep_args(XM_RL_A2C, XM_RL_GRAD, 1)
-        a.theta, a.theta_task_stride = _p(adapted), P
-        a.out, a.out_task_stride, a.scale = _p(self.bar), P, 1.0
-        self._launch(a)
+        self.a2c_grad(adapted, P, 1, self.bar)
         if first_order:
             return valid, self._sum_tasks(self.bar), adapted
         self.hvp(theta, self.bar, P, self.pertask, head_only=3 if anil else 0)
         return valid, self._sum_tasks(self.pertask), adapted
+
+    def a2c_grad(self, theta, stride, k, out):
+        """out_t = d/d theta_t of the a2c loss of replay k (weights ``coef[k]``) at ``theta`` ([P] shared, stride 0, or
+        [tasks, P])."""
+        a = self._sweep_args(XM_RL_A2C, XM_RL_GRAD, k)
+        a.theta, a.theta_task_stride = _p(theta), stride
+        a.out, a.out_task_stride, a.scale = _p(out), self.P, 1.0
+        self._launch(a)
+        return out
 
     def _sum_tasks(self, per_task):
         out = torch.empty(self.P, dtype=torch.float32, device=self.device)

@@ -129,20 +129,23 @@ def fast_adapt_ppo(params, support, query, cfg, anil=False, activation=torch.tan
 
 
 def fast_adapt_vpg(params, support, query, cfg, anil=False, first_order=False, activation=torch.tanh):
-    """core_functions/rl.py:208-254 on fixed replays, one adaptation step: ``vpg_a2c_loss`` is ``a2c.policy_loss`` of the
-    learner's log-probabilities against the GAE advantages of a freshly fitted baseline -- NOT normalised (unlike
-    ``trpo_a2c_loss``, rl.py:355) -- ``learner.adapt(loss, first_order, allow_unused=anil)`` is one MAML step, and the
-    validation loss is the same loss of the adapted learner on the query replay.  ANIL: the body runs under no_grad
-    during the inner loss (``turn_off_body_grads``) and its parameters stay un-adapted; the query loss sees the whole
-    network.  Returns (validation loss with graph, adapted parameter list)."""
+    """core_functions/rl.py:208-254 on fixed replays: ``vpg_a2c_loss`` is ``a2c.policy_loss`` of the learner's
+    log-probabilities against the GAE advantages of a freshly fitted baseline -- NOT normalised (unlike
+    ``trpo_a2c_loss``, rl.py:355) -- ``learner.adapt(loss, first_order, allow_unused=anil)`` is one MAML step per support
+    replay (``support``: one replay or a list, one per adaptation step), and the validation loss is the same loss of the
+    adapted learner on the query replay.  ANIL: the body runs under no_grad during the inner losses
+    (``turn_off_body_grads``) and its parameters stay un-adapted; the query loss sees the whole network.
+    Returns (validation loss with graph, adapted parameter list)."""
     def lp(ps, rep, body_no_grad=False):
         mean = policy_mean_anil(ps, rep['states'], activation, body_no_grad) if anil else policy_mean(ps, rep['states'], activation)
         scale = torch.exp(torch.clamp(ps[0], min=math.log(EPSILON)))
         return Normal(loc=mean, scale=scale).log_prob(rep['actions']).mean(dim=1, keepdim=True)
-    adv = compute_advantages(support, cfg['tau'], cfg['gamma'], cfg['value_reg'])
-    loss = ch.a2c_policy_loss(lp(params, support, anil), adv)
-    grads = torch.autograd.grad(loss, params, retain_graph=not first_order, create_graph=not first_order, allow_unused=anil)
-    new = [p if g is None else p - cfg['inner_lr'] * g for p, g in zip(params, grads)]
+    new = list(params)
+    for rep in (support if isinstance(support, (list, tuple)) else [support]):
+        adv = compute_advantages(rep, cfg['tau'], cfg['gamma'], cfg['value_reg'])
+        loss = ch.a2c_policy_loss(lp(new, rep, anil), adv)
+        grads = torch.autograd.grad(loss, new, retain_graph=not first_order, create_graph=not first_order, allow_unused=anil)
+        new = [p if g is None else p - cfg['inner_lr'] * g for p, g in zip(new, grads)]
     adv_q = compute_advantages(query, cfg['tau'], cfg['gamma'], cfg['value_reg'])
     return ch.a2c_policy_loss(lp(new, query), adv_q), new
 

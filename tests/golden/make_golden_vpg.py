@@ -6,7 +6,7 @@
 The train half of one MAML-VPG / ANIL-VPG outer iteration (rl/maml_vpg.py, rl/anil_vpg.py) minus the environment: per task
 ``policy.clone()`` (learn2learn MAML restatement), the reference's unmodified ``core_functions/rl.py::fast_adapt_vpg``
 with a stub task whose ``run()`` returns the seeded synthetic replays, the mean validation loss, ``backward()``; second
-order and ``first_order=True``.  float64.  Before anything is written oracle/rl_oracle.py::fast_adapt_vpg must
+order and ``first_order=True``, one adaptation step and (keys ``*2``) two.  float64.  Before anything is written oracle/rl_oracle.py::fast_adapt_vpg must
 reproduce the run (validation losses, adapted parameters, meta-gradient)."""
 import os
 import sys
@@ -29,10 +29,10 @@ TASKS, EPISODES, HORIZON, SEED = 3, 4, 25, 3
 
 
 class StubTask:
-    """``task.run(learner, episodes=...)``: first call the support replay, second call the query replay."""
-    def __init__(self, ch, sup, qry):
+    """``task.run(learner, episodes=...)``: the support replays in order (one per adaptation step), then the query replay."""
+    def __init__(self, ch, sups, qry):
         mk = lambda r: ch.Replay(r['states'], r['actions'], r['rewards'], r['dones'], r['next_states'])   # noqa: E731
-        self.queue = [mk(sup), mk(qry)]
+        self.queue = [mk(r) for r in sups] + [mk(qry)]
 
     def run(self, learner, episodes=None, render=False):
         return self.queue.pop(0)
@@ -45,9 +45,11 @@ def main():
     rl.get_ep_successes = lambda episodes, path_length: 0          # environment bookkeeping (success flags): not on the path
     torch.set_default_dtype(torch.float64)
     data = make_replays(TASKS, EPISODES, HORIZON, seed=SEED, dtype=torch.float64)
+    data2 = make_replays(TASKS, EPISODES, HORIZON, seed=SEED + 100, dtype=torch.float64)     # second-step support replays
     out = {}
-    for anil in (False, True):
-        for first_order in (False, True):
+    for anil, first_order, steps in ((False, False, 1), (False, True, 1), (True, False, 1), (True, True, 1),
+                                     (False, False, 2), (True, False, 2)):
+        if True:
             torch.manual_seed(42)
             policy = pol.DiagNormalPolicyANIL(2, 2, 100) if anil else pol.DiagNormalPolicy(2, 2, activation='tanh')
             policy = policy.double()
@@ -57,9 +59,11 @@ def main():
             baseline = ch.LinearValue(2, CFG['value_reg']).double()
             losses, adapted = [], []
             total = 0.0
-            for sup, qry in data:
+            cfg = dict(CFG, adapt_steps=steps)
+            sups = [[sup] if steps == 1 else [sup, data2[t][0]] for t, (sup, _q) in enumerate(data)]
+            for t, (_sup, qry) in enumerate(data):
                 learner = maml.clone()
-                loss, _rew, _suc = rl.fast_adapt_vpg(StubTask(ch, sup, qry), learner, baseline, CFG, anil=anil,
+                loss, _rew, _suc = rl.fast_adapt_vpg(StubTask(ch, sups[t], qry), learner, baseline, cfg, anil=anil,
                                                      first_order=first_order)
                 losses.append(float(loss))
                 adapted.append(torch.cat([p.detach().reshape(-1) for p in learner.module.parameters()]))
@@ -69,14 +73,14 @@ def main():
             # ---- the restatement must reproduce the reference-file run ------------------------------------------
             ps = [p.clone().requires_grad_() for p in theta0]
             tot = 0.0
-            for t, (sup, qry) in enumerate(data):
-                v, new = ro.fast_adapt_vpg(ps, sup, qry, CFG, anil=anil, first_order=first_order)
+            for t, (_sup, qry) in enumerate(data):
+                v, new = ro.fast_adapt_vpg(ps, sups[t], qry, CFG, anil=anil, first_order=first_order)
                 assert abs(float(v) - losses[t]) < 1e-10 * max(1.0, abs(losses[t])), (float(v), losses[t])
                 assert torch.allclose(torch.cat([x.detach().reshape(-1) for x in new]), adapted[t], rtol=1e-10, atol=1e-12)
                 tot = tot + v
             g_or = torch.cat([g.reshape(-1) for g in torch.autograd.grad(tot / TASKS, ps)])
             assert torch.allclose(g_or, grad, rtol=1e-9, atol=1e-10), (g_or - grad).abs().max()
-            key = ('anil' if anil else 'maml') + ('_fo' if first_order else '')
+            key = ('anil' if anil else 'maml') + ('_fo' if first_order else '') + ('2' if steps == 2 else '')
             out[key + '_theta0'] = torch.cat([p.reshape(-1) for p in theta0]).numpy()
             out[key + '_adapted'] = torch.stack(adapted).numpy()
             out[key + '_valid_loss'] = np.array(losses)
@@ -84,7 +88,7 @@ def main():
             print('%s: restatement == reference files; valid losses %s, |grad| %.3e'
                   % (key, np.round(losses, 6), float(grad.norm())))
     np.savez_compressed(os.path.join(HERE, 'rl', 'rl_vpg_small.npz'), tasks=TASKS, episodes=EPISODES, horizon=HORIZON,
-                        seed=SEED, **out)
+                        seed=SEED, seed2=SEED + 100, **out)
     print('wrote rl_vpg_small.npz')
 
 

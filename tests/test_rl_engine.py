@@ -245,25 +245,28 @@ def test_vpg_adaptation_and_meta_gradient_match_reference_fixture(kdev, anil, fi
 
 
 @pytest.mark.parametrize('anil', [False, True])
-def test_fast_adapt_vpg_reference_call_pattern(kdev, anil):
+@pytest.mark.parametrize('steps', [1, 2])
+def test_fast_adapt_vpg_reference_call_pattern(kdev, anil, steps):
     """rl/maml_vpg.py / rl/anil_vpg.py with the product's modules: policy.clone(), fast_adapt_vpg on a stub task
-    returning the fixture's replays, mean loss, backward() -> master .grad == the reference's."""
+    returning the fixture's replays (one or two adaptation steps), mean loss, backward() -> master .grad == the
+    reference's."""
     from exploring_meta_b200.core_functions import rl as xrl
     from exploring_meta_b200.core_functions.maml import MAML
     from exploring_meta_b200.core_functions.policies import DiagNormalPolicy, DiagNormalPolicyANIL, LinearValue
     g = np.load(GOLD_VPG)
-    key = 'anil' if anil else 'maml'
+    key = ('anil' if anil else 'maml') + ('2' if steps == 2 else '')
     tasks = int(g['tasks'])
     policy = (DiagNormalPolicyANIL(2, 2, 100) if anil else DiagNormalPolicy(2, 2, activation='tanh')).to(kdev)
     policy.load_flat_parameters(torch.from_numpy(g[key + '_theta0']).float().to(kdev))
     maml = MAML(policy, lr=VPG_CFG['inner_lr'])
     baseline = LinearValue(2, VPG_CFG['value_reg'])
-    params = dict(VPG_CFG, adapt_steps=1, adapt_batch_size=int(g['episodes']))
+    params = dict(VPG_CFG, adapt_steps=steps, adapt_batch_size=int(g['episodes']))
     data = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']))
+    data2 = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed2']))
 
     class StubTask:
-        def __init__(self, sup, qry):
-            self.queue = [sup, qry]
+        def __init__(self, queue):
+            self.queue = list(queue)
 
         def run(self, learner, episodes=None, render=False):
             return self.queue.pop(0)
@@ -271,18 +274,19 @@ def test_fast_adapt_vpg_reference_call_pattern(kdev, anil):
     total = 0.0
     for t, (sup, qry) in enumerate(data):
         learner = maml.clone()
-        loss, _rew, _suc = xrl.fast_adapt_vpg(StubTask(sup, qry), learner, baseline, params, anil=anil)
+        queue = [sup, qry] if steps == 1 else [sup, data2[t][0], qry]
+        loss, _rew, _suc = xrl.fast_adapt_vpg(StubTask(queue), learner, baseline, params, anil=anil)
         assert rel(learner.module.flat_parameters(), torch.from_numpy(g[key + '_adapted'][t])) < 1e-5
         assert abs(float(loss) - float(g[key + '_valid_loss'][t])) < 2e-5 * abs(float(g[key + '_valid_loss'][t])) + 1e-7
         total = total + loss
     (total / tasks).backward()
     grad = torch.cat([p.grad.reshape(-1) for p in policy.parameters()])
     assert rel(grad, torch.from_numpy(g[key + '_grad'])) < 2e-4
-    # value-only entry point: vpg_a2c_loss of the un-adapted policy on a support replay == the oracle
-    sup64 = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']), dtype=torch.float64)[0][0]
-    th64 = [p.requires_grad_() for p in _unflat64(g[key + '_theta0'])]
-    lp = ro.log_prob(th64, sup64['states'], sup64['actions']) if not anil else None
-    if lp is not None:
+    if steps == 1 and not anil:
+        # value-only entry point: vpg_a2c_loss of the un-adapted policy on a support replay == the oracle
+        sup64 = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']), dtype=torch.float64)[0][0]
+        th64 = [p.requires_grad_() for p in _unflat64(g[key + '_theta0'])]
+        lp = ro.log_prob(th64, sup64['states'], sup64['actions'])
         ref = ch.a2c_policy_loss(lp, ro.compute_advantages(sup64, VPG_CFG['tau'], VPG_CFG['gamma'], VPG_CFG['value_reg']))
         got = xrl.vpg_a2c_loss(data[0][0], policy, baseline, VPG_CFG['gamma'], VPG_CFG['tau'])
         assert abs(float(got) - float(ref)) < 2e-5 * abs(float(ref)) + 1e-7
