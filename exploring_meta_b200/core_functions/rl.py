@@ -165,33 +165,48 @@ class _PpoValidLoss(torch.autograd.Function):
 def fast_adapt_ppo(task, learner, baseline, params, anil=False, render=False):
     """rl.py:264-316.  ``learner`` = ``policy.clone()`` of a ``MAML``-wrapped ``DiagNormalPolicy`` /
     ``DiagNormalPolicyANIL``; ``task.run(learner, episodes=...)`` collects the replays (environment side,
-    caller-provided).  Returns ``(valid_loss, query_rew, query_success_rate)``; ``valid_loss.backward()`` accumulates
-    the second-order meta-gradient into the master policy like the reference's autograd graph does."""
-    if params.get('adapt_steps', 1) != 1:
-        raise NotImplementedError('one adaptation step (one support replay) per task')
+    caller-provided), one support replay per adaptation step, each followed by ``ppo_epochs`` clipped-PPO steps against
+    the log-probabilities of the policy the step started from.  Returns ``(valid_loss, query_rew,
+    query_success_rate)``; ``valid_loss.backward()`` accumulates the second-order meta-gradient into the master policy
+    like the reference's autograd graph does (the cotangent is carried back through the steps, last to first)."""
     policy = learner.module
     before = list(policy.parameters())                       # the clone's differentiable copies of the master
     dev = before[0].device
-    theta0 = torch.cat([p.detach().reshape(-1).float() for p in before])
+    theta = torch.cat([p.detach().reshape(-1).float() for p in before])
+    epochs, clip = params['ppo_epochs'], params['ppo_clip_ratio']
     if anil:
         policy.turn_off_body_grads()
-    support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
-    e = _engine(policy, baseline, 1, support['states'].shape[0], params['inner_lr'], params['gamma'], params['tau'], dev)
-    e.load_replays([[support, support]])
-    adapted = e.ppo_adapt(theta0, params['ppo_epochs'], params['ppo_clip_ratio'], anil)[0].clone()
-    # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the query rollouts
-    o = 0
-    for module in policy.modules():
-        for name, p in list(module._parameters.items()):
-            if p is not None:
-                module._parameters[name] = adapted[o:o + p.numel()].view_as(p)
-                o += p.numel()
+    supports, chains, e = [], [], None
+    for _step in range(params.get('adapt_steps', 1)):
+        support = _as_dict(task.run(learner, episodes=params['adapt_batch_size'], render=render))
+        e = _engine(policy, baseline, 1, support['states'].shape[0], params['inner_lr'], params['gamma'], params['tau'], dev)
+        e.load_replays([[support, support]])
+        theta = e.ppo_adapt(theta, epochs, clip, anil)[0].clone()
+        supports.append(support)
+        chains.append(e.ppo_thetas.clone())                   # theta_0 .. theta_E of this step
+        # re-bind the learner's parameters to the adapted values (what learner.adapt leaves behind) for the next rollouts
+        o = 0
+        for module in policy.modules():
+            for name, p in list(module._parameters.items()):
+                if p is not None:
+                    module._parameters[name] = theta[o:o + p.numel()].view_as(p)
+                    o += p.numel()
     if anil:
         policy.turn_on_body_grads()
     query_episodes = task.run(learner, episodes=params['adapt_batch_size'])
     query = _as_dict(query_episodes)
-    e.load_replays([[support, query]])
-    valid, grad = e.ppo_outer(params['ppo_epochs'], params['ppo_clip_ratio'], anil)
+    e.load_replays([[supports[-1], query]])
+    valid, grad = e.ppo_outer(epochs, clip, anil)             # back through the last step (its chain is still loaded)
+    if len(supports) > 1:
+        cur = e.ppo_task_grads
+        nxt = e.pertask if cur.data_ptr() == e.bar.data_ptr() else e.bar
+        for s in reversed(range(len(supports) - 1)):
+            e.load_replays([[supports[s], query]])
+            e.ppo_thetas.copy_(chains[s])
+            e.ppo_set_old()
+            cur = e.ppo_backprop(cur, nxt, epochs, clip, anil)
+            nxt = e.pertask if cur.data_ptr() == e.bar.data_ptr() else e.bar
+        grad = cur[0].clone()
     valid_loss = _PpoValidLoss.apply(valid[0], grad, *before)
     query_rew = query['rewards'].sum().item() / params['adapt_batch_size']
     return valid_loss, query_rew, 0.0

@@ -202,10 +202,7 @@ class TrpoEngine:
             self.logstd_old_s = torch.zeros(B, self.ad, dtype=torch.float32, device=self.device)
         th = self.ppo_thetas
         th[0].copy_(theta.expand(B, P) if theta.dim() == 1 else theta)
-        a = self._sweep_args(XM_RL_A2C, XM_RL_FORWARD, 0)          # old policy outputs on the support states
-        a.theta, a.theta_task_stride, a.mu_out = _p(th[0]), P, _p(self.mu_old_s)
-        self._launch(a)
-        self.logstd_old_s.copy_(torch.clamp(th[0][:, :self.ad], min=LOG_EPS))
+        self.ppo_set_old()
         for e in range(epochs):
             a = self._ppo_args(XM_RL_GRAD, e, clip)
             a.out, a.out_task_stride = _p(th[e + 1]), P
@@ -213,6 +210,30 @@ class TrpoEngine:
             a.head_only = 1 if anil else 0
             self._launch(a)
         return th[epochs]
+
+    def ppo_set_old(self):
+        """Outputs of the un-adapted policies ``ppo_thetas[0]`` on the loaded support states: the fixed old log-probabilities
+        of an adaptation step (no_grad, rl.py:281-282)."""
+        th0, P = self.ppo_thetas[0], self.P
+        a = self._sweep_args(XM_RL_A2C, XM_RL_FORWARD, 0)
+        a.theta, a.theta_task_stride, a.mu_out = _p(th0), P, _p(self.mu_old_s)
+        self._launch(a)
+        self.logstd_old_s.copy_(torch.clamp(th0[:, :self.ad], min=LOG_EPS))
+
+    def ppo_backprop(self, cur, nxt, epochs, clip, anil=False):
+        """Carries the cotangent ``cur`` [tasks, P] of theta_E back to theta_0 of ONE adaptation step (``ppo_thetas``,
+        old outputs and support replay of that step loaded): bar_e = bar_{e+1} - lr * M H_e (M bar_{e+1}).  Returns the
+        buffer holding bar_0 (``cur`` and ``nxt`` are used alternately)."""
+        P = self.P
+        for e in reversed(range(epochs)):
+            a = self._ppo_args(XM_RL_HVP, e, clip)
+            a.theta_dot, a.theta_dot_task_stride = _p(cur), P
+            a.out, a.out_task_stride = _p(nxt), P
+            a.base, a.base_task_stride, a.scale = _p(cur), P, -self.lr
+            a.head_only = 3 if anil else 0          # the inner-loop graph holds the head / sigma only (body under no_grad)
+            self._launch(a)
+            cur, nxt = nxt, cur
+        return cur
 
     def ppo_outer(self, epochs, clip, anil=False):
         """Validation loss of the adapted policies on the query replay (rl.py:297-309: the PPO objective against the
@@ -226,15 +247,7 @@ class TrpoEngine:
         a.out, a.out_task_stride, a.scale = _p(self.bar), P, 1.0
         self._launch(a)
         valid_loss = self.coef[1].sum(dim=1)
-        cur, nxt = self.bar, self.pertask
-        for e in reversed(range(epochs)):
-            a = self._ppo_args(XM_RL_HVP, e, clip)
-            a.theta_dot, a.theta_dot_task_stride = _p(cur), P
-            a.out, a.out_task_stride = _p(nxt), P
-            a.base, a.base_task_stride, a.scale = _p(cur), P, -self.lr
-            a.head_only = 3 if anil else 0          # the inner-loop graph holds the head / sigma only (body under no_grad)
-            self._launch(a)
-            cur, nxt = nxt, cur
+        cur = self.ppo_backprop(self.bar, self.pertask, epochs, clip, anil)
         self.ppo_task_grads = cur
         return valid_loss, self._sum_tasks(cur)
 

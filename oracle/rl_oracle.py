@@ -103,24 +103,25 @@ def policy_mean_anil(params, states, activation=torch.tanh, body_no_grad=False):
 
 
 def fast_adapt_ppo(params, support, query, cfg, anil=False, activation=torch.tanh):
-    """core_functions/rl.py:264-316 on fixed replays (the environment rollouts replaced by ``support`` / ``query``):
-    ``ppo_epochs`` inner steps of learn2learn ``adapt`` (second order) on the clipped PPO objective with the old
-    log-probabilities fixed at the un-adapted learner, then the PPO objective of the adapted learner on the query
-    replay against its own detached log-probabilities.  ANIL: the body runs under no_grad during the inner loop
-    (``turn_off_body_grads``) and ``allow_unused`` leaves its parameters un-adapted.  Returns (validation loss with
-    graph, adapted parameter list)."""
+    """core_functions/rl.py:264-316 on fixed replays (the environment rollouts replaced by ``support`` -- one replay or a
+    list, one per adaptation step -- and ``query``): per step ``ppo_epochs`` inner steps of learn2learn ``adapt`` (second
+    order) on the clipped PPO objective with the old log-probabilities fixed at the learner the step started from
+    (no_grad), then the PPO objective of the adapted learner on the query replay against its own detached
+    log-probabilities.  ANIL: the body runs under no_grad during the inner loop (``turn_off_body_grads``) and
+    ``allow_unused`` leaves its parameters un-adapted.  Returns (validation loss with graph, adapted parameter list)."""
     def lp(ps, rep, body_no_grad=False):
         mean = policy_mean_anil(ps, rep['states'], activation, body_no_grad) if anil else policy_mean(ps, rep['states'], activation)
         scale = torch.exp(torch.clamp(ps[0], min=math.log(EPSILON)))
         return Normal(loc=mean, scale=scale).log_prob(rep['actions']).mean(dim=1, keepdim=True)
-    adv = ch.normalize(compute_advantages(support, cfg['tau'], cfg['gamma'], cfg['value_reg'])).detach()
-    with torch.no_grad():
-        old_lp = lp(params, support, anil)
     new = list(params)
-    for _epoch in range(cfg['ppo_epochs']):
-        loss = ch.ppo_policy_loss(lp(new, support, anil), old_lp, adv, clip=cfg['ppo_clip_ratio'])
-        grads = torch.autograd.grad(loss, new, retain_graph=True, create_graph=True, allow_unused=anil)
-        new = [p if g is None else p - cfg['inner_lr'] * g for p, g in zip(new, grads)]
+    for rep in (support if isinstance(support, (list, tuple)) else [support]):
+        adv = ch.normalize(compute_advantages(rep, cfg['tau'], cfg['gamma'], cfg['value_reg'])).detach()
+        with torch.no_grad():
+            old_lp = lp(new, rep, anil)
+        for _epoch in range(cfg['ppo_epochs']):
+            loss = ch.ppo_policy_loss(lp(new, rep, anil), old_lp, adv, clip=cfg['ppo_clip_ratio'])
+            grads = torch.autograd.grad(loss, new, retain_graph=True, create_graph=True, allow_unused=anil)
+            new = [p if g is None else p - cfg['inner_lr'] * g for p, g in zip(new, grads)]
     adv_q = ch.normalize(compute_advantages(query, cfg['tau'], cfg['gamma'], cfg['value_reg'])).detach()
     with torch.no_grad():
         old_q = lp(new, query)

@@ -29,10 +29,10 @@ TASKS, EPISODES, HORIZON, SEED = 3, 4, 25, 2
 
 
 class StubTask:
-    """``task.run(learner, episodes=...)``: first call the support replay, second call the query replay."""
-    def __init__(self, ch, sup, qry):
+    """``task.run(learner, episodes=...)``: the support replays in order (one per adaptation step), then the query replay."""
+    def __init__(self, ch, sups, qry):
         mk = lambda r: ch.Replay(r['states'], r['actions'], r['rewards'], r['dones'], r['next_states'])   # noqa: E731
-        self.queue = [mk(sup), mk(qry)]
+        self.queue = [mk(r) for r in sups] + [mk(qry)]
 
     def run(self, learner, episodes=None, render=False):
         return self.queue.pop(0)
@@ -44,8 +44,11 @@ def main():
     rl.set_device(torch.device('cpu'))
     torch.set_default_dtype(torch.float64)
     data = make_replays(TASKS, EPISODES, HORIZON, seed=SEED, dtype=torch.float64)
+    data2 = make_replays(TASKS, EPISODES, HORIZON, seed=SEED + 100, dtype=torch.float64)     # second-step support replays
     out = {}
-    for anil in (False, True):
+    for anil, steps in ((False, 1), (True, 1), (False, 2), (True, 2)):
+        cfg = dict(CFG, adapt_steps=steps)
+        sups = [[sup] if steps == 1 else [sup, data2[t][0]] for t, (sup, _q) in enumerate(data)]
         torch.manual_seed(42)
         policy = pol.DiagNormalPolicyANIL(2, 2, 100) if anil else pol.DiagNormalPolicy(2, 2, activation='tanh')
         policy = policy.double()
@@ -55,9 +58,9 @@ def main():
         baseline = ch.LinearValue(2, CFG['value_reg']).double()
         losses, adapted = [], []
         total = 0.0
-        for sup, qry in data:
+        for t, (_sup, qry) in enumerate(data):
             learner = maml.clone()
-            loss, _rew, _suc = rl.fast_adapt_ppo(StubTask(ch, sup, qry), learner, baseline, CFG, anil=anil)
+            loss, _rew, _suc = rl.fast_adapt_ppo(StubTask(ch, sups[t], qry), learner, baseline, cfg, anil=anil)
             losses.append(float(loss))
             adapted.append(torch.cat([p.detach().reshape(-1) for p in learner.module.parameters()]))
             total = total + loss
@@ -66,21 +69,21 @@ def main():
         # ---- the restatement must reproduce the reference-file run ------------------------------------------
         ps = [p.clone().requires_grad_() for p in theta0]
         tot = 0.0
-        for t, (sup, qry) in enumerate(data):
-            v, new = ro.fast_adapt_ppo(ps, sup, qry, CFG, anil=anil)
+        for t, (_sup, qry) in enumerate(data):
+            v, new = ro.fast_adapt_ppo(ps, sups[t], qry, CFG, anil=anil)
             assert abs(float(v) - losses[t]) < 1e-12, (float(v), losses[t])
             assert torch.allclose(torch.cat([x.detach().reshape(-1) for x in new]), adapted[t], rtol=1e-10, atol=1e-12)
             tot = tot + v
         g_or = torch.cat([g.reshape(-1) for g in torch.autograd.grad(tot / TASKS, ps)])
         assert torch.allclose(g_or, grad, rtol=1e-9, atol=1e-12), (g_or - grad).abs().max()
-        key = 'anil' if anil else 'maml'
+        key = ('anil' if anil else 'maml') + ('2' if steps == 2 else '')
         out[key + '_theta0'] = torch.cat([p.reshape(-1) for p in theta0]).numpy()
         out[key + '_adapted'] = torch.stack(adapted).numpy()
         out[key + '_valid_loss'] = np.array(losses)
         out[key + '_grad'] = grad.numpy()
         print('%s: restatement == reference files; valid losses %s, |grad| %.3e' % (key, np.round(losses, 6), float(grad.norm())))
     np.savez_compressed(os.path.join(HERE, 'rl', 'rl_ppo_small.npz'), tasks=TASKS, episodes=EPISODES, horizon=HORIZON,
-                        seed=SEED, **out)
+                        seed=SEED, seed2=SEED + 100, **out)
     print('wrote rl_ppo_small.npz')
 
 

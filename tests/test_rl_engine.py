@@ -179,25 +179,28 @@ def test_ppo_inner_loop_and_meta_gradient_match_reference_fixture(kdev, anil):
 
 
 @pytest.mark.parametrize('anil', [False, True])
-def test_fast_adapt_ppo_reference_call_pattern(kdev, anil):
+@pytest.mark.parametrize('steps', [1, 2])
+def test_fast_adapt_ppo_reference_call_pattern(kdev, anil, steps):
     """rl/maml_ppo.py:103-129 / rl/anil_ppo.py:106-130 with the product's modules: policy.clone(), fast_adapt_ppo on a
-    stub task returning the fixture's replays, mean loss, backward() -> master .grad == the reference's."""
+    stub task returning the fixture's replays (one or two adaptation steps), mean loss, backward() -> master .grad ==
+    the reference's."""
     from exploring_meta_b200.core_functions import rl as xrl
     from exploring_meta_b200.core_functions.maml import MAML
     from exploring_meta_b200.core_functions.policies import DiagNormalPolicy, DiagNormalPolicyANIL, LinearValue
     g = np.load(GOLD_PPO)
-    key = 'anil' if anil else 'maml'
+    key = ('anil' if anil else 'maml') + ('2' if steps == 2 else '')
     tasks = int(g['tasks'])
     policy = (DiagNormalPolicyANIL(2, 2, 100) if anil else DiagNormalPolicy(2, 2, activation='tanh')).to(kdev)
     policy.load_flat_parameters(torch.from_numpy(g[key + '_theta0']).float().to(kdev))
     maml = MAML(policy, lr=PPO_CFG['inner_lr'])
     baseline = LinearValue(2, PPO_CFG['value_reg'])
-    params = dict(PPO_CFG, adapt_steps=1, adapt_batch_size=int(g['episodes']))
+    params = dict(PPO_CFG, adapt_steps=steps, adapt_batch_size=int(g['episodes']))
     data = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed']))
+    data2 = make_replays(tasks, int(g['episodes']), int(g['horizon']), seed=int(g['seed2']))
 
     class StubTask:
-        def __init__(self, sup, qry):
-            self.queue = [sup, qry]
+        def __init__(self, queue):
+            self.queue = list(queue)
 
         def run(self, learner, episodes=None, render=False):
             return self.queue.pop(0)
@@ -205,7 +208,8 @@ def test_fast_adapt_ppo_reference_call_pattern(kdev, anil):
     total = 0.0
     for t, (sup, qry) in enumerate(data):
         learner = maml.clone()
-        loss, _rew, _suc = xrl.fast_adapt_ppo(StubTask(sup, qry), learner, baseline, params, anil=anil)
+        queue = [sup, qry] if steps == 1 else [sup, data2[t][0], qry]
+        loss, _rew, _suc = xrl.fast_adapt_ppo(StubTask(queue), learner, baseline, params, anil=anil)
         assert rel(learner.module.flat_parameters(), torch.from_numpy(g[key + '_adapted'][t])) < 1e-5
         total = total + loss
     (total / tasks).backward()
